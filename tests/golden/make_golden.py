@@ -1,0 +1,158 @@
+"""Generate the committed golden fixtures under tests/golden/.
+
+Run HERE (the authoring container), never on the GPU box:
+
+    python tests/golden/make_golden.py
+
+1. ``deform_*.npz`` -- produced by the REFERENCE'S OWN code imported from
+   /root/reference: ``flow3d.params.GaussianParams`` / ``MotionBases``
+   (params.py:10-180), ``flow3d.transforms.cont_6d_to_rmat``
+   (transforms.py:41-53) and the unbound ``SceneModel.compute_poses_fg`` /
+   ``compute_poses_all`` / ``compute_transforms`` methods
+   (scene_model.py:67-120), plus the camera sub-exposure transform lines
+   (scene_model.py:352-353) restated verbatim below.  Third-party modules that
+   are absent here are stubbed in ``sys.modules``: ``roma`` by
+   ``oracle/roma_shim.py`` (a restatement), ``gsplat`` / ``pypose`` /
+   ``jaxtyping`` / ``cv2`` by empty placeholders (never called on this path).
+   Gradients are torch autograd of that reference code for fixed cotangents.
+
+2. ``raster_*.npz`` -- produced by ``oracle/raster.py`` (the C oracle) on the
+   seeded synthetic scenes.  These are NOT reference outputs (gsplat cannot be
+   run here: "parity unpinned"); they freeze the oracle so that a later edit
+   of the oracle cannot silently move the target.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from deblur4dgs_b200.synthetic import make_scene  # noqa: E402
+from oracle import roma_shim  # noqa: E402
+
+
+def _import_reference():
+    sys.modules["roma"] = roma_shim
+    g = types.ModuleType("gsplat")
+    gr = types.ModuleType("gsplat.rendering")
+    gr.rasterization = None
+    g.rendering = gr
+    sys.modules["gsplat"] = g
+    sys.modules["gsplat.rendering"] = gr
+    pp = types.ModuleType("pypose")
+    pp.LieTensor = object
+    sys.modules["pypose"] = pp
+    jt = types.ModuleType("jaxtyping")
+    jt.Float = type("Float", (), {"__class_getitem__": classmethod(lambda cls, k: cls)})
+    sys.modules["jaxtyping"] = jt
+    if "cv2" not in sys.modules:
+        try:
+            import cv2  # noqa: F401
+        except Exception:
+            sys.modules["cv2"] = types.ModuleType("cv2")
+    sys.path.insert(0, "/root/reference")
+    from flow3d.params import GaussianParams, MotionBases
+    from flow3d.scene_model import SceneModel
+    return GaussianParams, MotionBases, SceneModel
+
+
+def deform_golden(name, G, K, N, seed, int_ts=False, out_of_range=False):
+    GaussianParams, MotionBases, SceneModel = _import_reference()
+    sc = make_scene(G=G, width=64, height=48, K=K, N=N, seed=seed)
+    if out_of_range:
+        sc.times = torch.linspace(-0.75, 8.25, N)  # exercises the clamp of floor/ceil (params.py:152-153)
+    t = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sc.tensors().items()}
+    fg = GaussianParams(t["fg_means"], t["fg_quats"], t["fg_scales"], t["fg_colors"], t["fg_opacities"],
+                        motion_coefs=t["motion_coefs"])
+    bg = GaussianParams(t["bg_means"], t["bg_quats"], t["bg_scales"], t["bg_colors"], t["bg_opacities"])
+    mb = MotionBases(t["rots"], t["transls"])
+    # a stand-in for `self` carrying exactly what the unbound methods touch
+    me = types.SimpleNamespace(fg=fg, bg=bg, motion_bases=mb, has_bg=True)
+    me.compute_transforms = lambda ts, inds=None: SceneModel.compute_transforms(me, ts, inds)
+    me.compute_poses_fg = lambda ts, inds=None: SceneModel.compute_poses_fg(me, ts, inds)
+    me.compute_poses_bg = lambda: SceneModel.compute_poses_bg(me)
+    times = t["times"]
+    RTs = t["RTs"]
+    leaves = dict(fg_means=fg.params["means"], fg_quats=fg.params["quats"], motion_coefs=fg.params["motion_coefs"],
+                  bg_means=bg.params["means"], bg_quats=bg.params["quats"], rots=mb.params["rots"],
+                  transls=mb.params["transls"], times=times, RTs=RTs)
+    out = {}
+    # (i) compute_transforms at B timestamps at once (trainer.py:478,485 style call)
+    ts_b = times.detach().clone()
+    if int_ts:
+        ts_b = torch.arange(0, min(N, 8))
+    transfms = SceneModel.compute_transforms(me, ts_b)
+    out["transforms_ts"] = ts_b.numpy()
+    out["transforms"] = transfms.detach().numpy()
+    # (ii) the render loop body for every sub-exposure (scene_model.py:323-353)
+    all_m, all_q = [], []
+    for ii in range(N):
+        time = times[None, ii:ii + 1]
+        means, quats = SceneModel.compute_poses_all(me, time)
+        means, quats = means[:, 0], quats[:, 0]
+        transR, transT = RTs[ii][:3, :3], RTs[ii][:3, 3:4]
+        means = transR @ means.permute(1, 0) + transT
+        means = means.permute(1, 0)
+        all_m.append(means)
+        all_q.append(quats)
+    M, Q = torch.stack(all_m), torch.stack(all_q)
+    out["out_means"], out["out_quats"] = M.detach().numpy(), Q.detach().numpy()
+    g = torch.Generator().manual_seed(seed + 100)
+    vM, vQ = torch.randn(M.shape, generator=g), torch.randn(Q.shape, generator=g)
+    out["v_out_means"], out["v_out_quats"] = vM.numpy(), vQ.numpy()
+    grads = torch.autograd.grad((M * vM).sum() + (Q * vQ).sum(), list(leaves.values()), allow_unused=True)
+    for k, gr in zip(leaves.keys(), grads):
+        out["grad_" + k] = gr.detach().numpy()
+        out["in_" + k] = leaves[k].detach().numpy()
+    np.savez_compressed(os.path.join(HERE, f"deform_{name}.npz"), **out)
+    print("wrote deform_%s.npz" % name, {k: v.shape for k, v in out.items() if k.startswith("out")})
+
+
+def raster_golden(name, G, W, H, seed, d0, mode, scale_mult=1.0, C=1):
+    from oracle import raster as orc
+    sc = make_scene(G=G, width=W, height=H, K=4, N=1, seed=seed, scale_mult=scale_mult)
+    means = torch.cat([sc.fg_means, sc.bg_means]).numpy()
+    quats = torch.cat([sc.fg_quats, sc.bg_quats]).numpy()
+    scales, opac, colors = sc.scales_all().numpy(), sc.opacities_all().numpy(), sc.colors_all(d0).numpy()
+    vm = sc.w2c.repeat(C, 1, 1).numpy().copy()
+    for c in range(1, C):
+        vm[c, 0, 3] = 0.15 * c
+        vm[c, 2, 3] = 0.1 * c
+    Ks = sc.K.repeat(C, 1, 1).numpy()
+    g = torch.Generator().manual_seed(seed + 7)
+    bg = torch.rand(C, d0, generator=g).numpy()
+    rc, ra, meta = orc.rasterization(means, quats, scales, opac, colors, vm, Ks, W, H, backgrounds=bg,
+                                     render_mode=mode)
+    vc = torch.randn(rc.shape, generator=g).numpy()
+    va = torch.randn(ra.shape, generator=g).numpy()
+    grads = orc.rasterization_backward(meta, ra, vc, va)
+    out = dict(means=means, quats=quats, scales=scales, opacities=opac, colors=colors, viewmats=vm, Ks=Ks,
+               backgrounds=bg, width=W, height=H, render_mode=mode,
+               render_colors=rc.astype(np.float16 if False else np.float32), render_alphas=ra,
+               radii=meta["radii"], means2d=meta["means2d"], depths=meta["depths"], conics=meta["conics"],
+               tiles_per_gauss=meta["tiles_per_gauss"], isect_ids=meta["isect_ids"],
+               flatten_ids=meta["flatten_ids"], isect_offsets=meta["isect_offsets"], last_ids=meta["last_ids"],
+               edge=meta["edge"], v_render_colors=vc, v_render_alphas=va)
+    for k, v in grads.items():
+        if v is not None:
+            out["grad_" + k] = v.astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, f"raster_{name}.npz"), **out)
+    print("wrote raster_%s.npz" % name, "n_isects", meta["isect_ids"].shape[0], "edge px", int(meta["edge"].sum()))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    deform_golden("k6_n5", G=600, K=6, N=5, seed=11)
+    deform_golden("k10_n9", G=900, K=10, N=9, seed=12)
+    deform_golden("k3_n1_int", G=257, K=3, N=1, seed=13, int_ts=True)
+    deform_golden("k16_n13_oob", G=300, K=16, N=13, seed=14, out_of_range=True)
+    raster_golden("small_rgb", G=500, W=96, H=64, seed=21, d0=3, mode="RGB", scale_mult=3.0)
+    raster_golden("small_ed5", G=800, W=112, H=80, seed=22, d0=4, mode="RGB+ED", scale_mult=2.0)
+    raster_golden("small_ed17_c2", G=700, W=100, H=70, seed=23, d0=16, mode="RGB+ED", scale_mult=2.5, C=2)
