@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Deblur4DGS render hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c3]
+
+Metric (BASELINE.json): rendered sub-exposure frames / s at 720x1280, 300k Gaussians,
+forward + backward.  One STEP = one blurry frame of config c3: motion-basis deformation at
+N=9 sub-exposure timestamps -> projection -> tile binning + radix sort -> blend (D=17
+channels, "RGB+ED") -> N-way combine, then the backward of all of it for fixed cotangents on
+the combined image and alpha.  One step therefore renders N=9 sub-exposure frames.
+
+N > 1 GPUs (torchrun, one rank per GPU): "frames" sharding -- every rank renders its own
+blurry frame (weak scaling) and the parameter gradients are SUM all-reduced over NCCL inside
+the timed region.  ``--shard subexposures`` runs BASELINE configs[3] instead (one frame's N
+sub-exposures dealt to the ranks; strong scaling).
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU oracle (the restatement of
+the reference's path -- gsplat is CUDA-only, so the reference has no CPU implementation of its
+own) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rendered sub-exposure frames/sec at 720x1280, 300k Gaussians (fwd+bwd)"
+UNIT = "frames/s"
+D0 = 16  # rgb(3) + fg mask(1) + 4x3 track channels; +1 expected depth => D = 17 (scene_model.py:205-296)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ #
+# algorithmic bytes -- per sub-exposure frame, fp32, C = 1
+# ------------------------------------------------------------------------------------------ #
+def algorithmic_bytes(G, Gf, K, D, P, I_per_frame, tiles):
+    I = I_per_frame
+    b = {}
+    b["deform_fwd"] = 4 * (Gf * K + 7 * G) + 4 * 7 * G
+    b["project_fwd"] = 40 * G + 28 * G
+    b["bin"] = 4 * G + 12 * I + 24 * I + 8 * I + 4 * tiles
+    b["blend_fwd"] = I * (28 + 4 * D) + P * 4 * (D + 2)
+    b["blend_bwd"] = I * (28 + 4 * D) + P * 4 * (D + 3) + G * 4 * (6 + D)
+    b["project_bwd"] = 68 * G + 24 * G + 40 * G
+    b["deform_bwd"] = 4 * (Gf * K + 7 * G) + 28 * G + 4 * (Gf * K + 7 * G)
+    return b
+
+
+# ------------------------------------------------------------------------------------------ #
+# CPU arm: the oracle restatement on the host cores
+# ------------------------------------------------------------------------------------------ #
+def cpu_frame(sc, d0, sub_idx=0):
+    """One sub-exposure frame forward + backward on the CPU: reference-style deformation
+    (oracle/deform.py, torch CPU) + oracle rasterizer (C/OpenMP).  Returns seconds."""
+    import numpy as np
+    from oracle import deform as odef
+    from oracle import raster as orc
+    t0 = time.perf_counter()
+    leaves = [t.clone().requires_grad_(True) for t in (sc.fg_means, sc.fg_quats, sc.motion_coefs, sc.bg_means,
+                                                       sc.bg_quats, sc.rots, sc.transls)]
+    M, Q = odef.deform_subexposures(*leaves, sc.times[sub_idx:sub_idx + 1], sc.RTs[sub_idx:sub_idx + 1])
+    scales, opac, colors = sc.scales_all().numpy(), sc.opacities_all().numpy(), sc.colors_all(d0).numpy()
+    rc, ra, meta = orc.rasterization(M[0].detach().numpy(), Q[0].detach().numpy(), scales, opac, colors,
+                                     sc.w2c.numpy(), sc.K.numpy(), sc.width, sc.height,
+                                     backgrounds=np.zeros((1, d0), np.float32), render_mode="RGB+ED")
+    g = orc.rasterization_backward(meta, ra, np.ones_like(rc), np.ones_like(ra), want_viewmats=False)
+    vM = torch.from_numpy(g["means"].astype("float32"))[None]
+    vQ = torch.from_numpy(g["quats"].astype("float32"))[None]
+    torch.autograd.backward([M, Q], [vM, vQ])
+    return time.perf_counter() - t0, int(meta["isect_ids"].shape[0])
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from deblur4dgs_b200.synthetic import make_config
+    from oracle import raster as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc.set_num_threads(cores)
+    sc = make_config(args.config)
+    for _ in range(min(args.warmup, 1)):
+        cpu_frame(sc, D0, 0)
+    ts = []
+    steps = max(1, args.steps)
+    for k in range(steps):
+        dt, n_isects = cpu_frame(sc, D0, k % sc.N)
+        ts.append(dt)
+    total = sum(ts)
+    value = steps / total
+    sample = f"{steps} step(s) x 1 sub-exposure frame fwd+bwd of config {args.config} (oracle deformation in torch CPU + C/OpenMP rasterizer)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded, SURVEY 8d)",
+            "config": workload_config(args, sc),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "gsplat (the reference's rasterizer) is CUDA-only; this arm times the CPU oracle port"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sc):
+    return {"workload": f"{args.config}: {sc.width}x{sc.height}, G={sc.G} (fg {sc.num_fg}), K={sc.rots.shape[0]}, "
+                        f"N={sc.N} sub-exposures, D={D0 + 1} channels (RGB+ED), fwd+bwd",
+            "shard": args.shard, "l2": "per-step working set (N x H x W x D image stack, 564 MB at c3) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ #
+# GPU arm
+# ------------------------------------------------------------------------------------------ #
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c5"])
+    ap.add_argument("--shard", default="frames", choices=["frames", "subexposures"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    from deblur4dgs_b200 import _cabi
+    from deblur4dgs_b200.parallel import allreduce_sum_, render_frame_sharded, shard_indices
+    from deblur4dgs_b200.scene import render_subexposures
+    from deblur4dgs_b200.synthetic import CONFIGS, make_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+
+    # every rank gets its own frame in "frames" mode (different seed offset => different view/time)
+    G, W, H, K, N, seed = CONFIGS[args.config]
+    sc_cpu = make_config(args.config, seed=seed + (rank if args.shard == "frames" else 0))
+    host = {k: v.pin_memory() for k, v in sc_cpu.tensors().items()}
+    sc = sc_cpu.to(dev)
+    P = W * H
+    Dtot = D0 + 1
+    bg = torch.zeros(1, D0, device=dev)
+    g = torch.Generator().manual_seed(1234)
+    w_img = torch.randn(1, H, W, Dtot, generator=g).to(dev)
+    w_acc = torch.randn(1, H, W, 1, generator=g).to(dev)
+    param_names = ["fg_means", "fg_quats", "fg_scales", "fg_colors", "fg_opacities", "motion_coefs", "bg_means",
+                   "bg_quats", "bg_scales", "bg_colors", "bg_opacities", "rots", "transls"]
+
+    def step(scn, want_outputs=False):
+        """One blurry frame forward + backward from the raw scene parameters."""
+        p = {k: getattr(scn, k).detach().requires_grad_(True) for k in param_names}
+        scales = torch.exp(torch.cat([p["fg_scales"], p["bg_scales"]], 0))
+        opac = torch.sigmoid(torch.cat([p["fg_opacities"], p["bg_opacities"]], 0))
+        rgb = torch.sigmoid(torch.cat([p["fg_colors"], p["bg_colors"]], 0))
+        mask = torch.zeros(scn.G, 1, device=dev)
+        mask[: scn.num_fg] = 1.0
+        colors = torch.cat([rgb, mask, scn.extra_channels], dim=-1)
+
+        def local(times, RTs, combine):
+            return render_subexposures(p["fg_means"], p["fg_quats"], p["motion_coefs"], p["bg_means"], p["bg_quats"],
+                                       p["rots"], p["transls"], times, RTs, scales, opac, colors, scn.w2c, scn.K, W, H,
+                                       backgrounds=bg, render_mode="RGB+ED", combine=combine, ref_quirk=True)
+
+        if world > 1 and args.shard == "subexposures":
+            def render_local(t, r):
+                o = local(t, r, False)
+                step.n_isects = int(o["meta"]["isect_ids"].numel())
+                return o["exposure_imgs"], o["exposure_alphas"]
+            img, acc = render_frame_sharded({}, scn.times, scn.RTs, render_local)
+        else:
+            o = local(scn.times, scn.RTs, True)
+            step.n_isects = int(o["meta"]["isect_ids"].numel())
+            img, acc = o["img"], o["acc"]
+        torch.autograd.backward([img, acc], [w_img, w_acc])
+        grads = [p[k].grad for k in param_names]
+        if world > 1:
+            allreduce_sum_(grads)
+        return (img, acc, grads) if want_outputs else None
+
+    frames_per_step_local = N if (world == 1 or args.shard == "frames") else len(shard_indices(N, rank, world))
+    frames_per_step_global = N * world if args.shard == "frames" else N
+
+    for _ in range(args.warmup):
+        step(sc)
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: kernel-resident throughput (inputs already in HBM) ----------------
+    prof = {}
+    _cabi.PROFILE = prof  # per-C-ABI-call CUDA events on the launching stream (see _cabi.call)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(sc)
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    _cabi.PROFILE = None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in prof.items()}
+    launches_per_step = sum(len(v) * _cabi.LAUNCHES.get(k, 1) for k, v in prof.items()) / args.steps
+    n_sort_passes = math.ceil((32 + _cabi.lib().d4_tile_n_bits(math.ceil(W / 16) * math.ceil(H / 16)) +
+                               int(math.floor(math.log2(frames_per_step_local))) + 1) / 8)
+    launches_per_step += (3 * n_sort_passes - 1)  # d4_sort_pairs_u64 launches 3 kernels per pass
+
+    # ---- timed region 2: end to end through the public API with HOST buffers --------------
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = None
+
+    def e2e_step():
+        nonlocal out_host
+        scn = type(sc)(**{k: v.to(dev, non_blocking=True) for k, v in host.items()}, width=W, height=H)
+        img, acc, grads = step(scn, want_outputs=True)
+        outs = [img, acc] + grads
+        if out_host is None:
+            out_host = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
+        for h, o in zip(out_host, outs):
+            h.copy_(o, non_blocking=True)
+
+    e2e_step()
+    torch.cuda.synchronize()
+    d2h_bytes = sum(h.numel() * h.element_size() for h in out_host)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = frames_per_step_global * args.steps / (float(ms2.item()) * 1e-3)
+
+    if rank == 0:
+        value = frames_per_step_global * args.steps / (ms_total * 1e-3)
+        I_total = step.n_isects  # intersections of this rank's launch (all local sub-exposures)
+        I_frame = I_total / max(1, frames_per_step_local)
+        tiles = math.ceil(W / 16) * math.ceil(H / 16)
+        ab = algorithmic_bytes(sc.G, sc.num_fg, K, Dtot, P, I_frame, tiles)
+        peak, peak_src = peaks()
+        dom = "d4_blend_bwd"
+        dom_ms = kernel_ms.get(dom, float("nan"))
+        dom_bytes = ab["blend_bwd"] * frames_per_step_local
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        step_bytes = sum(ab.values()) * frames_per_step_local
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak" if args.shard == "frames" else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded, SURVEY 8d); random-init scene, no dataset/checkpoint",
+            "config": workload_config(args, sc),
+            "n_isects_per_frame": I_frame,
+            "roofline": {"bound": "hbm", "kernel": "blend_bwd_kernel<17> (d4_blend_bwd)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                         "note": "blend is fp32-issue/MUFU/shuffle bound, not HBM bound (DESIGN.md); whole-step "
+                                 "algorithmic-bytes rate is in step_hbm"},
+            "step_hbm": {"algorithmic_bytes_per_step": step_bytes,
+                         "achieved_gbs": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
+                         "frac_of_peak": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak},
+            "kernel_ms_per_step": {k: v * len(prof[k]) / args.steps for k, v in kernel_ms.items()},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": float(ms2.item()) / args.steps},
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import raster as orc
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            orc.set_num_threads(cores)
+            cpu_frame(sc_cpu, D0, 0)  # warm-up (page-in, OpenMP pool)
+            n_cpu = 2
+            dts = [cpu_frame(sc_cpu, D0, i)[0] for i in range(n_cpu)]
+            line["cpu_baseline"] = {"value": n_cpu / sum(dts), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_cpu} sub-exposure frames fwd+bwd of {args.config} (1 warm-up), oracle port "
+                                              "(torch-CPU deformation + C/OpenMP rasterizer), all host cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,324 @@
+// binning.cu -- row a9 of SURVEY.md section 8: the integer half of tile binning.
+//   d4_exclusive_scan_i32 : cumsum of tiles_per_gauss   (torch.cumsum in gsplat.isect_tiles)
+//   d4_sort_pairs_u64     : stable LSD radix sort        (cub::DeviceRadixSort in gsplat)
+//   d4_tile_offsets       : gsplat.isect_offset_encode
+//
+// All three are HBM-bound integer passes.  Layout: keys u64 / values u32 as two
+// separate streams (SoA), 2048 pairs per CTA, 8 bits per pass.  Per pass:
+//   (1) per-CTA digit histogram            -> hist[digit][cta]      (digit-major)
+//   (2) 256 CTAs scan their digit's row    -> exclusive per-CTA offsets + digit totals
+//   (3) stable scatter: warp-level multi-split with __match_any_sync gives each
+//       key its rank among equal digits; CTA-level digit bases come from (2).
+// No decoupled look-back / spin-waiting anywhere: every kernel is a plain
+// bulk-synchronous pass, so a scheduling surprise cannot hang the device.
+#include "common.cuh"
+
+namespace d4 {
+
+// ----------------------------------------------------------------------------- scan
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int64_t block_sum_i64(int64_t v, int64_t *smem /*[8]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    int64_t t = 0;
+#pragma unroll
+    for (int i = 0; i < kScanThreads / 32; ++i) t += smem[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_block_sums_kernel(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ block_sums) {
+    __shared__ int64_t sm[kScanThreads / 32];
+    int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        int64_t j = base + (int64_t)i * kScanThreads + threadIdx.x;
+        if (j < n) acc += in[j];
+    }
+    int64_t t = block_sum_i64(acc, sm);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const int32_t *__restrict__ in, int64_t n, const int64_t *__restrict__ block_sums,
+                  int32_t *__restrict__ out, int64_t *__restrict__ total) {
+    __shared__ int64_t sm[kScanThreads / 32];
+    __shared__ int32_t warp_tot[kScanThreads / 32];
+    // prefix of all earlier CTAs (each CTA re-reduces the short block_sums array)
+    int64_t acc = 0;
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += kScanThreads) acc += block_sums[j];
+    int64_t prefix = block_sum_i64(acc, sm);
+    // local exclusive scan: thread t owns items [t*8, t*8+8) of the tile
+    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int32_t v[kScanItems];
+    int32_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        tsum += v[i];
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    int32_t woff = 0;
+#pragma unroll
+    for (int i = 0; i < kScanThreads / 32; ++i)
+        if (i < w) woff += warp_tot[i];
+    int64_t run = prefix + woff + (incl - tsum);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (base + i < n) out[base + i] = (int32_t)run;
+        run += v[i];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total = run;
+}
+
+// ----------------------------------------------------------------------------- radix sort
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 pairs per CTA
+constexpr int kRadix = 256;
+
+__global__ void __launch_bounds__(kSortThreads)
+sort_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t mask, int nblocks,
+                 uint32_t *__restrict__ hist /*[256][nblocks]*/) {
+    __shared__ uint32_t h[kRadix];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        int64_t j = base + (int64_t)i * kSortThreads + threadIdx.x;
+        if (j < n) atomicAdd(&h[(uint32_t)(keys[j] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// one CTA per digit: exclusive scan of that digit's per-CTA counts (in place) + digit total
+__global__ void __launch_bounds__(kSortThreads)
+sort_scan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict__ digit_total) {
+    __shared__ uint32_t warp_tot[kSortThreads / 32];
+    __shared__ uint32_t carry_s;
+    uint32_t *row = hist + (int64_t)blockIdx.x * nblocks;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int start = 0; start < nblocks; start += kSortThreads) {
+        int j = start + threadIdx.x;
+        uint32_t v = (j < nblocks) ? row[j] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        uint32_t woff = 0, chunk = 0;
+#pragma unroll
+        for (int i = 0; i < kSortThreads / 32; ++i) {
+            uint32_t t = warp_tot[i];
+            if (i < w) woff += t;
+            chunk += t;
+        }
+        uint32_t carry = carry_s;
+        if (j < nblocks) row[j] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + chunk;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) digit_total[blockIdx.x] = carry_s;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+sort_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                    uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
+                    int shift, uint32_t mask, int nblocks, const uint32_t *__restrict__ hist,
+                    const uint32_t *__restrict__ digit_total) {
+    __shared__ uint32_t warp_cnt[kSortThreads / 32][kRadix];
+    __shared__ uint32_t digit_off[kRadix];
+    __shared__ uint32_t warp_tot[kSortThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < kSortThreads / 32; ++i) warp_cnt[i][tid] = 0;
+
+    // global base of digit `tid`: exclusive scan of the 256 digit totals
+    {
+        uint32_t v = digit_total[tid];
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int i = 0; i < kSortThreads / 32; ++i)
+            if (i < w) woff += warp_tot[i];
+        digit_off[tid] = woff + incl - v + hist[(int64_t)tid * nblocks + blockIdx.x];
+    }
+    __syncthreads();
+
+    // each warp owns a contiguous run of 256 pairs, item i of lane l at run + i*32 + l:
+    // processing items in order i = 0..7 visits the run in memory order => stable.
+    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (32 * kSortItems);
+    uint64_t key[kSortItems];
+    uint32_t val[kSortItems];
+    uint32_t rank[kSortItems];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        int64_t j = wbase + i * 32 + lane;
+        bool valid = j < n;
+        key[i] = valid ? keys_in[j] : 0ull;
+        val[i] = valid ? vals_in[j] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        int64_t j = wbase + i * 32 + lane;
+        bool valid = j < n;
+        uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        uint32_t d_eff = valid ? d : (kRadix + lane);  // out-of-range lanes match nobody
+        uint32_t peers = __match_any_sync(0xffffffffu, d_eff);
+        uint32_t before = __popc(peers & lt_mask);
+        uint32_t base = valid ? warp_cnt[w][d] : 0u;
+        __syncwarp();
+        if (valid && before == 0) warp_cnt[w][d] = base + __popc(peers);
+        __syncwarp();
+        rank[i] = base + before;
+    }
+    __syncthreads();
+    // turn per-warp counts into exclusive offsets over warps (digit = tid)
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int i = 0; i < kSortThreads / 32; ++i) {
+            uint32_t t = warp_cnt[i][tid];
+            warp_cnt[i][tid] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        int64_t j = wbase + i * 32 + lane;
+        if (j < n) {
+            uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            uint32_t pos = digit_off[d] + warp_cnt[w][d] + rank[i];
+            keys_out[pos] = key[i];
+            vals_out[pos] = val[i];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- tile offsets
+__global__ void __launch_bounds__(256)
+tile_offsets_kernel(const int64_t *__restrict__ ids, int64_t n, int n_tiles, int tile_n_bits,
+                    int64_t total, int32_t *__restrict__ offsets) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int64_t tmask = (1LL << tile_n_bits) - 1;
+    int64_t hi = ids[idx] >> 32;
+    int64_t cur = (hi >> tile_n_bits) * n_tiles + (hi & tmask);
+    if (idx == 0)
+        for (int64_t t = 0; t <= cur && t < total; ++t) offsets[t] = 0;
+    int64_t nxt = total;
+    if (idx + 1 < n) {
+        int64_t h2 = ids[idx + 1] >> 32;
+        nxt = (h2 >> tile_n_bits) * n_tiles + (h2 & tmask);
+    }
+    for (int64_t t = cur + 1; t <= nxt && t < total; ++t) offsets[t] = (int32_t)(idx + 1);
+}
+
+}  // namespace d4
+
+using namespace d4;
+
+extern "C" size_t d4_scan_workspace_bytes(int64_t n) {
+    return sizeof(int64_t) * (size_t)(cdiv(n > 0 ? n : 1, kScanTile) + 1);
+}
+
+extern "C" int d4_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out_exclusive, int64_t *total,
+                                     void *workspace, size_t workspace_bytes, d4_stream_t stream) {
+    D4_CHECK_ARG(n >= 0 && total, "d4_exclusive_scan_i32: bad arguments");
+    if (n == 0) {
+        cudaMemsetAsync(total, 0, sizeof(int64_t), as_stream(stream));
+        return 0;
+    }
+    D4_CHECK_ARG(in && out_exclusive && workspace && workspace_bytes >= d4_scan_workspace_bytes(n),
+                 "d4_exclusive_scan_i32: null pointer or workspace too small");
+    int nb = cdiv(n, kScanTile);
+    int64_t *bs = reinterpret_cast<int64_t *>(workspace);
+    scan_block_sums_kernel<<<nb, kScanThreads, 0, as_stream(stream)>>>(in, n, bs);
+    scan_apply_kernel<<<nb, kScanThreads, 0, as_stream(stream)>>>(in, n, bs, out_exclusive, total);
+    D4_CHECK_LAUNCH("d4_exclusive_scan_i32");
+    return 0;
+}
+
+extern "C" size_t d4_sort_workspace_bytes(int64_t n) {
+    int nb = cdiv(n > 0 ? n : 1, kSortTile);
+    return sizeof(uint32_t) * ((size_t)kRadix * nb + kRadix);
+}
+
+extern "C" int d4_sort_pairs_u64(uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint32_t *vals_b,
+                                 int64_t n, int begin_bit, int end_bit, void *workspace,
+                                 size_t workspace_bytes, int *result_in_b, d4_stream_t stream) {
+    D4_CHECK_ARG(n >= 0 && n < (1LL << 31) && begin_bit >= 0 && end_bit <= 64 && begin_bit <= end_bit && result_in_b,
+                 "d4_sort_pairs_u64: bad arguments");
+    *result_in_b = 0;
+    if (n <= 1 || begin_bit == end_bit) return 0;
+    D4_CHECK_ARG(keys_a && vals_a && keys_b && vals_b && workspace && workspace_bytes >= d4_sort_workspace_bytes(n),
+                 "d4_sort_pairs_u64: null pointer or workspace too small");
+    int nb = cdiv(n, kSortTile);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(workspace);
+    uint32_t *dtot = hist + (size_t)kRadix * nb;
+    uint64_t *ki = keys_a, *ko = keys_b;
+    uint32_t *vi = vals_a, *vo = vals_b;
+    int flips = 0;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        int bits = end_bit - shift < 8 ? end_bit - shift : 8;
+        uint32_t mask = (1u << bits) - 1u;
+        sort_hist_kernel<<<nb, kSortThreads, 0, as_stream(stream)>>>(ki, n, shift, mask, nb, hist);
+        sort_scan_kernel<<<kRadix, kSortThreads, 0, as_stream(stream)>>>(hist, nb, dtot);
+        sort_scatter_kernel<<<nb, kSortThreads, 0, as_stream(stream)>>>(ki, vi, ko, vo, n, shift, mask, nb, hist, dtot);
+        uint64_t *tk = ki; ki = ko; ko = tk;
+        uint32_t *tv = vi; vi = vo; vo = tv;
+        ++flips;
+    }
+    D4_CHECK_LAUNCH("d4_sort_pairs_u64");
+    *result_in_b = flips & 1;
+    return 0;
+}
+
+extern "C" int d4_tile_offsets(const int64_t *isect_ids_sorted, int64_t n_isects, int C, int tile_w, int tile_h,
+                               int32_t *offsets, d4_stream_t stream) {
+    D4_CHECK_ARG(offsets && C >= 1 && tile_w >= 1 && tile_h >= 1 && n_isects >= 0, "d4_tile_offsets: bad arguments");
+    int64_t total = (int64_t)C * tile_w * tile_h;
+    if (n_isects == 0) {
+        cudaMemsetAsync(offsets, 0, sizeof(int32_t) * total, as_stream(stream));
+        return 0;
+    }
+    D4_CHECK_ARG(isect_ids_sorted, "d4_tile_offsets: null pointer");
+    int tb = d4_tile_n_bits(tile_w * tile_h);
+    tile_offsets_kernel<<<cdiv(n_isects, 256), 256, 0, as_stream(stream)>>>(isect_ids_sorted, n_isects,
+                                                                           tile_w * tile_h, tb, total, offsets);
+    D4_CHECK_LAUNCH("d4_tile_offsets");
+    return 0;
+}

@@ -1,0 +1,489 @@
+// blend.cu -- rows a10 / a11 of SURVEY.md section 8: per-tile alpha compositing.
+//   d4_blend_fwd : gsplat rasterize_to_pixels fwd (+ depth channel, + ED normalisation)
+//   d4_blend_bwd : gsplat rasterize_to_pixels bwd (+ ED normalisation backward)
+//
+// One CTA per (camera, 16x16 tile), 256 threads = 256 pixels; each WARP owns a
+// compact 8x4 pixel block (not a 16x2 strip) so that a Gaussian's footprint
+// touches as few warps as possible and whole warps skip it after one vote.
+// Gaussians of the tile are staged 256 at a time into shared memory
+// (xy+opacity, conic, D colour channels, id); the per-pair loop reads them as
+// warp-wide broadcasts.
+//
+// Backward, per (warp, Gaussian): the D+6 partial sums of the 32 pixels are
+// reduced with a TRANSPOSING butterfly (31 shuffles for up to 32 values instead
+// of 5 per value), added to a per-CTA shared-memory accumulator and flushed to
+// HBM once per (tile, Gaussian) -- one global atomic per value per tile instead
+// of one per warp.  The per-pixel recurrences are carried as scalars:
+//   s_i = <c_i, v_out>,  S = sum_{j>i} s_j alpha_j T_j,
+//   dL/dalpha_i = T_i s_i - (S + T_final (bg.v_out - v_alpha_out)) / (1 - alpha_i)
+// which is algebraically gsplat's per-channel buffer[] form with D fewer
+// registers and D fewer FMAs per pair.
+//
+// These kernels are bound by fp32 issue + MUFU.EX2 + shuffle throughput, not by
+// HBM: algorithmic bytes per (pixel, Gaussian) pair are ~0.4.
+#include "common.cuh"
+
+namespace d4 {
+
+constexpr int kTile = 16;
+constexpr int kBlendThreads = kTile * kTile;
+constexpr int kBatch = kBlendThreads;
+
+template <int D>
+struct BlendCfg {
+    static constexpr int DS = (D + 3) / 4 * 4;  // smem colour stride (float4 aligned)
+    static constexpr int DP = D | 1;            // odd stride for conflict-free per-pixel staging
+    static constexpr int V = D + 6;             // per-Gaussian gradient values
+};
+
+struct BlendArgs {
+    const float *means2d, *conics, *opacities, *colors, *depths, *backgrounds;
+    int64_t colors_cs;
+    int C, G, D0, width, height, tile_w, tile_h;
+    const int32_t *tile_offsets, *flatten_ids;
+    int64_t n_isects;
+    int normalize_depth;
+};
+
+// pixel owned by this thread: warp w -> 8x4 block (w&1, w>>1), lane -> (lane&7, lane>>3)
+__device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
+    int w = tid >> 5, lane = tid & 31;
+    lx = (w & 1) * 8 + (lane & 7);
+    ly = (w >> 1) * 4 + (lane >> 3);
+}
+
+// stage one batch: thread tr loads Gaussian `idx` (if in range) into slot tr
+template <int D>
+__device__ __forceinline__ void stage_gaussian(const BlendArgs &a, int c, int64_t idx, bool in_range, int tr,
+                                               float4 *s_geom, float4 *s_conic, float *s_col) {
+    constexpr int DS = BlendCfg<D>::DS;
+    if (!in_range) return;
+    int32_t g = __ldg(a.flatten_ids + idx);
+    int32_t gl = g - c * a.G;
+    float2 xy = __ldg(reinterpret_cast<const float2 *>(a.means2d) + g);
+    float opac = __ldg(a.opacities + gl);
+    s_geom[tr] = make_float4(xy.x, xy.y, opac, __int_as_float(g));
+    const float *cp = a.conics + 3LL * g;
+    s_conic[tr] = make_float4(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), 0.f);
+    const float *col = a.colors + c * a.colors_cs + (int64_t)gl * a.D0;
+    float *dst = s_col + tr * DS;
+    const int d0 = a.depths ? D - 1 : D;
+    if ((d0 & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < D / 4; ++k) {
+            if (4 * k < d0) {
+                float4 v = __ldg(reinterpret_cast<const float4 *>(col) + k);
+                *reinterpret_cast<float4 *>(dst + 4 * k) = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if (k < d0) dst[k] = __ldg(col + k);
+    }
+    if (a.depths) dst[D - 1] = __ldg(a.depths + g);
+}
+
+// ----------------------------------------------------------------------------- forward
+template <int D>
+__global__ void __launch_bounds__(kBlendThreads)
+blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restrict__ render_alphas,
+                 int32_t *__restrict__ last_ids, float *__restrict__ acc_depth) {
+    constexpr int DS = BlendCfg<D>::DS;
+    constexpr int DP = BlendCfg<D>::DP;
+    __shared__ float4 s_geom[kBatch];
+    __shared__ float4 s_conic[kBatch];
+    __shared__ __align__(16) float s_col[kBatch * (DS > DP ? DS : DP)];
+
+    const int n_tiles = a.tile_w * a.tile_h;
+    const int ct = blockIdx.x;
+    const int c = ct / n_tiles;
+    const int tile = ct - c * n_tiles;
+    const int ty = tile / a.tile_w, tx = tile - ty * a.tile_w;
+    const int tid = threadIdx.x;
+    int lx, ly;
+    pixel_of_thread(tid, lx, ly);
+    const int j = tx * kTile + lx, i = ty * kTile + ly;
+    const bool inside = (i < a.height) && (j < a.width);
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int64_t pid = ((int64_t)c * a.height + i) * a.width + j;
+
+    const int64_t range_start = a.tile_offsets[ct];
+    const int64_t range_end = (ct == a.C * n_tiles - 1) ? a.n_isects : (int64_t)a.tile_offsets[ct + 1];
+    const int num_batches = (int)((range_end - range_start + kBatch - 1) / kBatch);
+
+    float T = 1.0f;
+    int32_t cur_idx = 0;
+    bool done = !inside;
+    float out[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) out[k] = 0.f;
+
+    for (int b = 0; b < num_batches; ++b) {
+        if (__syncthreads_count(done) >= kBlendThreads) break;
+        const int64_t batch_start = range_start + (int64_t)kBatch * b;
+        stage_gaussian<D>(a, c, batch_start + tid, batch_start + tid < range_end, tid, s_geom, s_conic, s_col);
+        __syncthreads();
+        const int batch_size = (int)min((int64_t)kBatch, range_end - batch_start);
+        for (int t = 0; t < batch_size; ++t) {
+            const float4 g0 = s_geom[t];
+            const float4 cn = s_conic[t];
+            const float dx = g0.x - px, dy = g0.y - py;
+            const float sigma = 0.5f * (cn.x * dx * dx + cn.z * dy * dy) + cn.y * dx * dy;
+            const float alpha = fminf(kAlphaMax, g0.z * __expf(-sigma));
+            const bool valid = !done && sigma >= 0.f && alpha >= kAlphaMin;
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            if (valid) {
+                const float next_T = T * (1.0f - alpha);
+                if (next_T <= kTMin) {
+                    done = true;
+                } else {
+                    const float vis = alpha * T;
+                    const float *cp = s_col + t * DS;
+#pragma unroll
+                    for (int k4 = 0; k4 < D / 4; ++k4) {
+                        const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
+                        out[4 * k4 + 0] = fmaf(cv.x, vis, out[4 * k4 + 0]);
+                        out[4 * k4 + 1] = fmaf(cv.y, vis, out[4 * k4 + 1]);
+                        out[4 * k4 + 2] = fmaf(cv.z, vis, out[4 * k4 + 2]);
+                        out[4 * k4 + 3] = fmaf(cv.w, vis, out[4 * k4 + 3]);
+                    }
+#pragma unroll
+                    for (int k = D / 4 * 4; k < D; ++k) out[k] = fmaf(cp[k], vis, out[k]);
+                    cur_idx = (int32_t)(batch_start + t);
+                    T = next_T;
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+
+    // epilogue: background, ED normalisation, coalesced store through shared memory
+    const float alpha_out = 1.0f - T;
+    if (a.backgrounds) {
+        const int d0 = a.depths ? D - 1 : D;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if (k < d0) out[k] = fmaf(T, __ldg(a.backgrounds + (int64_t)c * a.D0 + k), out[k]);
+    }
+    if (inside) {
+        render_alphas[pid] = alpha_out;
+        last_ids[pid] = cur_idx;
+        if (a.normalize_depth) {
+            acc_depth[pid] = out[D - 1];
+            out[D - 1] = out[D - 1] / fmaxf(alpha_out, 1e-10f);
+        }
+    }
+    __syncthreads();  // everyone is done reading s_col
+    {
+        float *dst = s_col + (ly * kTile + lx) * DP;
+#pragma unroll
+        for (int k = 0; k < D; ++k) dst[k] = out[k];
+    }
+    __syncthreads();
+    const int row_elems = kTile * D;
+    for (int e = tid; e < kTile * row_elems; e += kBlendThreads) {
+        const int r = e / row_elems, col = e - r * row_elems;
+        const int pxl = col / D, k = col - pxl * D;
+        const int gi = ty * kTile + r, gj = tx * kTile + pxl;
+        if (gi < a.height && gj < a.width)
+            render_colors[(((int64_t)c * a.height + gi) * a.width + gj) * D + k] = s_col[(r * kTile + pxl) * DP + k];
+    }
+}
+
+// ----------------------------------------------------------------------------- backward
+// Transposing butterfly: v[0..NV) per lane -> v[0] = sum over the warp of value (lane & (NV-1)).
+template <int NV>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[NV], int lane) {
+#pragma unroll
+    for (int h = NV / 2; h >= 1; h >>= 1) {
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float lo = v[i], hi = v[i + h];
+            const float send = upper ? lo : hi;
+            const float keep = upper ? hi : lo;
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+#pragma unroll
+    for (int o = NV; o < 32; o <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+
+template <int V>
+struct RedWidth {
+    static constexpr int value = V <= 8 ? 8 : (V <= 16 ? 16 : 32);
+};
+
+template <int D>
+__global__ void __launch_bounds__(kBlendThreads)
+blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
+                 const float *__restrict__ acc_depth, const float *__restrict__ v_render_colors,
+                 const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
+                 float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opacities,
+                 float *__restrict__ v_depths) {
+    constexpr int DS = BlendCfg<D>::DS;
+    constexpr int V = BlendCfg<D>::V;
+    constexpr int VS = V | 1;  // odd accumulator stride
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_geom = reinterpret_cast<float4 *>(smem_raw);
+    float4 *s_conic = s_geom + kBatch;
+    float *s_col = reinterpret_cast<float *>(s_conic + kBatch);
+    float *s_acc = s_col + kBatch * DS;
+    __shared__ int32_t s_max[kBlendThreads / 32];
+
+    const int n_tiles = a.tile_w * a.tile_h;
+    const int ct = blockIdx.x;
+    const int c = ct / n_tiles;
+    const int tile = ct - c * n_tiles;
+    const int ty = tile / a.tile_w, tx = tile - ty * a.tile_w;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int lx, ly;
+    pixel_of_thread(tid, lx, ly);
+    const int j = tx * kTile + lx, i = ty * kTile + ly;
+    const bool inside = (i < a.height) && (j < a.width);
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int64_t pid = ((int64_t)c * a.height + i) * a.width + j;
+
+    const int64_t range_start = a.tile_offsets[ct];
+    int64_t range_end = (ct == a.C * n_tiles - 1) ? a.n_isects : (int64_t)a.tile_offsets[ct + 1];
+    if (range_end <= range_start) return;  // uniform for the CTA
+
+    // per-pixel state
+    float v_out[D];
+    float T_final = 1.f, v_ra = 0.f;
+    int32_t bin_final = -1;
+    if (inside) {
+        const float alpha_px = render_alphas[pid];
+        T_final = 1.0f - alpha_px;
+        bin_final = last_ids[pid];
+        v_ra = v_render_alphas[pid];
+#pragma unroll
+        for (int k = 0; k < D; ++k) v_out[k] = __ldg(v_render_colors + pid * D + k);
+        if (a.normalize_depth) {
+            const float ac = fmaxf(alpha_px, 1e-10f);
+            const float vd = v_out[D - 1];
+            v_out[D - 1] = vd / ac;
+            if (alpha_px > 1e-10f) v_ra += -vd * acc_depth[pid] / (ac * ac);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) v_out[k] = 0.f;
+    }
+    float bgdot = 0.f;
+    if (a.backgrounds) {
+        const int d0 = a.depths ? D - 1 : D;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if (k < d0) bgdot = fmaf(__ldg(a.backgrounds + (int64_t)c * a.D0 + k), v_out[k], bgdot);
+    }
+    // constant part of dL/dalpha_i * (1 - alpha_i):  T_final * (v_alpha_out - bg.v_out)
+    const float tail = T_final * (v_ra - bgdot);
+    float T = T_final;
+    float S = 0.f;  // sum_{j>i} <c_j, v_out> alpha_j T_j
+
+    // nothing behind the last contributing Gaussian of any pixel of the CTA matters
+    const int32_t warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
+    if (lane == 0) s_max[w] = warp_bin_final;
+    __syncthreads();
+    int32_t block_bin_final = s_max[0];
+#pragma unroll
+    for (int k = 1; k < kBlendThreads / 32; ++k) block_bin_final = max(block_bin_final, s_max[k]);
+    range_end = min(range_end, (int64_t)block_bin_final + 1);
+    if (range_end <= range_start) return;
+    const int num_batches = (int)((range_end - range_start + kBatch - 1) / kBatch);
+
+    constexpr int RW = RedWidth<V>::value;
+    constexpr int NCHUNK = (V + 31) / 32;
+    constexpr int RN = NCHUNK == 1 ? RW : NCHUNK * 32;
+
+    for (int b = 0; b < num_batches; ++b) {
+        __syncthreads();  // previous batch fully consumed (s_* reuse) and flushed
+        const int64_t batch_end = range_end - 1 - (int64_t)kBatch * b;  // slot 0 = furthest back
+        const int batch_size = (int)min((int64_t)kBatch, batch_end + 1 - range_start);
+        stage_gaussian<D>(a, c, batch_end - tid, batch_end - tid >= range_start, tid, s_geom, s_conic, s_col);
+        for (int e = tid; e < kBatch * VS; e += kBlendThreads) s_acc[e] = 0.f;
+        __syncthreads();
+
+        int t0 = (int)max((int64_t)0, batch_end - (int64_t)warp_bin_final);
+        for (int t = t0; t < batch_size; ++t) {
+            const float4 g0 = s_geom[t];
+            const float4 cn = s_conic[t];
+            const float dx = g0.x - px, dy = g0.y - py;
+            const float sigma = 0.5f * (cn.x * dx * dx + cn.z * dy * dy) + cn.y * dx * dy;
+            const float vis = __expf(-sigma);
+            const float alpha = fminf(kAlphaMax, g0.z * vis);
+            const bool valid = (batch_end - t <= (int64_t)bin_final) && sigma >= 0.f && alpha >= kAlphaMin;
+            if (!__any_sync(0xffffffffu, valid)) continue;
+
+            float r[RN];
+#pragma unroll
+            for (int k = 0; k < RN; ++k) r[k] = 0.f;
+            if (valid) {
+                const float ra = 1.0f / (1.0f - alpha);
+                T *= ra;
+                const float fac = alpha * T;
+                const float *cp = s_col + t * DS;
+                float s = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < D / 4; ++k4) {
+                    const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
+                    s = fmaf(cv.x, v_out[4 * k4 + 0], s);
+                    s = fmaf(cv.y, v_out[4 * k4 + 1], s);
+                    s = fmaf(cv.z, v_out[4 * k4 + 2], s);
+                    s = fmaf(cv.w, v_out[4 * k4 + 3], s);
+                }
+#pragma unroll
+                for (int k = D / 4 * 4; k < D; ++k) s = fmaf(cp[k], v_out[k], s);
+#pragma unroll
+                for (int k = 0; k < D; ++k) r[k] = fac * v_out[k];
+                const float v_alpha = s * T - (S - tail) * ra;
+                S = fmaf(s, fac, S);
+                if (g0.z * vis <= kAlphaMax) {
+                    const float v_sigma = -g0.z * vis * v_alpha;
+                    r[D + 0] = 0.5f * v_sigma * dx * dx;
+                    r[D + 1] = v_sigma * dx * dy;
+                    r[D + 2] = 0.5f * v_sigma * dy * dy;
+                    r[D + 3] = v_sigma * (cn.x * dx + cn.y * dy);
+                    r[D + 4] = v_sigma * (cn.y * dx + cn.z * dy);
+                    r[D + 5] = vis * v_alpha;
+                }
+            }
+            // warp reduction of the V partial sums, then CTA-level accumulation
+            if constexpr (NCHUNK == 1) {
+                warp_transpose_reduce<RN>(r, lane);
+                const int slot = lane & (RW - 1);
+                if (lane < RW && slot < V) atomicAdd(&s_acc[t * VS + slot], r[0]);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < NCHUNK; ++ch) {
+                    float rr[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) rr[k] = r[ch * 32 + k];
+                    warp_transpose_reduce<32>(rr, lane);
+                    const int slot = ch * 32 + lane;
+                    if (slot < V) atomicAdd(&s_acc[t * VS + slot], rr[0]);
+                }
+            }
+        }
+        __syncthreads();
+        // flush: one global atomic per non-zero (Gaussian, value) of this tile
+        const int d0 = a.depths ? D - 1 : D;
+        for (int e = tid; e < batch_size * V; e += kBlendThreads) {
+            const int t = e / V, k = e - t * V;
+            const float val = s_acc[t * VS + k];
+            if (val == 0.f) continue;
+            const int32_t g = __float_as_int(s_geom[t].w);
+            const int32_t gl = g - c * a.G;
+            float *dst;
+            if (k < d0) dst = v_colors + c * a.colors_cs + (int64_t)gl * a.D0 + k;
+            else if (k < D) dst = v_depths + g;
+            else if (k < D + 3) dst = v_conics + 3LL * g + (k - D);
+            else if (k < D + 5) dst = v_means2d + 2LL * g + (k - D - 3);
+            else dst = v_opacities + gl;
+            atomicAdd(dst, val);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- dispatch
+template <int D>
+static int launch_fwd(const BlendArgs &a, float *rc, float *ra, int32_t *li, float *ad, cudaStream_t st) {
+    int grid = a.C * a.tile_w * a.tile_h;
+    blend_fwd_kernel<D><<<grid, kBlendThreads, 0, st>>>(a, rc, ra, li, ad);
+    return 0;
+}
+template <int D>
+static int launch_bwd(const BlendArgs &a, const float *ra, const int32_t *li, const float *ad, const float *vrc,
+                      const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd, cudaStream_t st) {
+    int grid = a.C * a.tile_w * a.tile_h;
+    constexpr size_t smem = sizeof(float4) * 2 * kBatch + sizeof(float) * kBatch * (BlendCfg<D>::DS + (BlendCfg<D>::V | 1));
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(blend_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return 1;
+        configured = true;
+    }
+    blend_bwd_kernel<D><<<grid, kBlendThreads, smem, st>>>(a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd);
+    return 0;
+}
+
+#define D4_FOR_EACH_D(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(16) X(17) X(32) X(33)
+
+}  // namespace d4
+
+using namespace d4;
+
+static int check_blend_args(const char *name, const BlendArgs &a, int tile_size) {
+    D4_CHECK_ARG(tile_size == kTile, "%s: only tile_size 16 is built", name);
+    D4_CHECK_ARG(a.C >= 1 && a.G >= 0 && a.D0 >= 0 && a.width > 0 && a.height > 0, "%s: bad sizes", name);
+    D4_CHECK_ARG(a.tile_w == (a.width + kTile - 1) / kTile && a.tile_h == (a.height + kTile - 1) / kTile,
+                 "%s: tile grid does not match the image size", name);
+    D4_CHECK_ARG(a.means2d && a.conics && a.opacities && a.tile_offsets && (a.flatten_ids || a.n_isects == 0),
+                 "%s: null pointer", name);
+    D4_CHECK_ARG(a.colors || a.D0 == 0, "%s: null colors", name);
+    D4_CHECK_ARG(((uintptr_t)a.means2d & 7) == 0, "%s: means2d must be 8-byte aligned", name);
+    if ((a.D0 & 3) == 0 && a.D0 > 0)
+        D4_CHECK_ARG(((uintptr_t)a.colors & 15) == 0 && (a.colors_cs & 3) == 0, "%s: colors must be 16-byte aligned", name);
+    return 0;
+}
+
+extern "C" int d4_blend_fwd(const float *means2d, const float *conics, const float *opacities,
+                            const float *colors, int64_t colors_cam_stride, const float *depths,
+                            const float *backgrounds, int C, int G, int D0, int width, int height,
+                            int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets,
+                            const int32_t *flatten_ids, int64_t n_isects, int normalize_depth,
+                            float *render_colors, float *render_alphas, int32_t *last_ids, float *acc_depth,
+                            d4_stream_t stream) {
+    BlendArgs a{means2d, conics, opacities, colors, depths, backgrounds, colors_cam_stride, C, G, D0, width,
+                height, tile_w, tile_h, tile_offsets, flatten_ids, n_isects, normalize_depth};
+    if (int rc = check_blend_args("d4_blend_fwd", a, tile_size)) return rc;
+    D4_CHECK_ARG(render_colors && render_alphas && last_ids, "d4_blend_fwd: null output");
+    D4_CHECK_ARG(!normalize_depth || (depths && acc_depth), "d4_blend_fwd: normalize_depth needs depths and acc_depth");
+    const int D = D0 + (depths ? 1 : 0);
+    switch (D) {
+#define X(n) case n: launch_fwd<n>(a, render_colors, render_alphas, last_ids, acc_depth, as_stream(stream)); break;
+        D4_FOR_EACH_D(X)
+#undef X
+        default:
+            set_error("d4_blend_fwd: channel count D=%d not built (pad to one of 1-9,16,17,32,33)", D);
+            return 2;
+    }
+    D4_CHECK_LAUNCH("d4_blend_fwd");
+    return 0;
+}
+
+extern "C" int d4_blend_bwd(const float *means2d, const float *conics, const float *opacities,
+                            const float *colors, int64_t colors_cam_stride, const float *depths,
+                            const float *backgrounds, int C, int G, int D0, int width, int height,
+                            int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets,
+                            const int32_t *flatten_ids, int64_t n_isects, int normalize_depth,
+                            const float *render_alphas, const int32_t *last_ids, const float *acc_depth,
+                            const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
+                            float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
+                            d4_stream_t stream) {
+    BlendArgs a{means2d, conics, opacities, colors, depths, backgrounds, colors_cam_stride, C, G, D0, width,
+                height, tile_w, tile_h, tile_offsets, flatten_ids, n_isects, normalize_depth};
+    if (int rc = check_blend_args("d4_blend_bwd", a, tile_size)) return rc;
+    D4_CHECK_ARG(render_alphas && last_ids && v_render_colors && v_render_alphas && v_means2d && v_conics &&
+                     v_opacities && (v_colors || D0 == 0),
+                 "d4_blend_bwd: null pointer");
+    D4_CHECK_ARG(!depths || v_depths, "d4_blend_bwd: v_depths required when depths is given");
+    D4_CHECK_ARG(!normalize_depth || (depths && acc_depth), "d4_blend_bwd: normalize_depth needs depths and acc_depth");
+    if (n_isects == 0) return 0;
+    const int D = D0 + (depths ? 1 : 0);
+    switch (D) {
+#define X(n)                                                                                                   \
+    case n:                                                                                                    \
+        launch_bwd<n>(a, render_alphas, last_ids, acc_depth, v_render_colors, v_render_alphas, v_means2d,      \
+                      v_conics, v_colors, v_opacities, v_depths, as_stream(stream));                           \
+        break;
+        D4_FOR_EACH_D(X)
+#undef X
+        default:
+            set_error("d4_blend_bwd: channel count D=%d not built (pad to one of 1-9,16,17,32,33)", D);
+            return 2;
+    }
+    D4_CHECK_LAUNCH("d4_blend_bwd");
+    return 0;
+}

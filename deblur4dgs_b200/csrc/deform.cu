@@ -1,0 +1,430 @@
+// deform.cu -- rows a1-a6 of SURVEY.md section 8, fused over all N sub-exposures:
+// softmax(motion_coefs) -> K-basis blend at floor/ceil frames -> time lerp ->
+// Gram-Schmidt -> R mu + t, quat(R) (x) q -> camera sub-exposure transform.
+// The reference spends ~40 elementwise/einsum launches per sub-exposure on this
+// (params.py:142-180, scene_model.py:76-120, 352-353); here the canonical
+// parameters are read ONCE for all N timestamps (4*(K+7) B per fg Gaussian) and
+// only the N deformed (mean, quat) pairs are written (28 B each): HBM-bound.
+//
+// Backward uses forward-mode dual numbers for the per-Gaussian SE(3) part (see
+// deform_math.cuh) and reduces the basis / time / camera gradients over
+// Gaussians with a transposing warp butterfly -> shared memory -> one global
+// atomic per CTA and value.
+#include "common.cuh"
+#include "deform_math.cuh"
+
+namespace d4 {
+
+constexpr int kDefThreads = 128;
+constexpr int kMaxK = 64;
+
+struct FramePair {
+    int pre, nxt;
+    float w;
+};
+
+__device__ __forceinline__ FramePair frame_pair(float t, int T) {
+    // params.py:152-153,173: indices clamped, weight from the clamped floor
+    FramePair f;
+    float lo = fminf(fmaxf(floorf(t), 0.f), (float)(T - 1));
+    float hi = fminf(fmaxf(ceilf(t), 0.f), (float)(T - 1));
+    f.pre = (int)lo;
+    f.nxt = (int)hi;
+    f.w = t - (float)f.pre;
+    return f;
+}
+
+// blended (transl 3, rot6d 6) at one frame: sum_k c_k * base[k, frame]
+__device__ __forceinline__ void blend_bases(const float *s_coef, int K, int T, int frame,
+                                            const float *__restrict__ rots,
+                                            const float *__restrict__ transls, float out[9]) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) out[j] = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float ck = s_coef[k * kDefThreads];
+        const float *tp = transls + ((int64_t)k * T + frame) * 3;
+        const float *rp = rots + ((int64_t)k * T + frame) * 6;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) out[j] += ck * __ldg(tp + j);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) out[3 + j] += ck * __ldg(rp + j);
+    }
+}
+
+// softmax over K raw logits of one Gaussian, result in s_coef[k * kDefThreads]
+__device__ __forceinline__ void softmax_coefs(const float *__restrict__ raw, int K, float *s_coef) {
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        float v = __ldg(raw + k);
+        s_coef[k * kDefThreads] = v;
+        mx = fmaxf(mx, v);
+    }
+    float sum = 0.f;
+    for (int k = 0; k < K; ++k) {
+        float e = expf(s_coef[k * kDefThreads] - mx);
+        s_coef[k * kDefThreads] = e;
+        sum += e;
+    }
+    for (int k = 0; k < K; ++k) s_coef[k * kDefThreads] = s_coef[k * kDefThreads] / sum;
+}
+
+__device__ __forceinline__ void apply_rt(const float *__restrict__ RT, const float m[3], float o[3]) {
+    if (RT == nullptr) {
+        o[0] = m[0]; o[1] = m[1]; o[2] = m[2];
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        o[i] = __ldg(RT + 4 * i) * m[0] + __ldg(RT + 4 * i + 1) * m[1] + __ldg(RT + 4 * i + 2) * m[2] + __ldg(RT + 4 * i + 3);
+}
+
+__global__ void __launch_bounds__(kDefThreads)
+deform_fg_fwd_kernel(const float *__restrict__ fg_means, const float *__restrict__ fg_quats,
+                     const float *__restrict__ coefs_raw, const float *__restrict__ rots,
+                     const float *__restrict__ transls, const float *__restrict__ times,
+                     const float *__restrict__ RTs, int Gf, int G, int K, int T, int N,
+                     float *__restrict__ out_means, float *__restrict__ out_quats) {
+    extern __shared__ float s_coef_all[];  // [K][kDefThreads]
+    int g = blockIdx.x * kDefThreads + threadIdx.x;
+    if (g >= Gf) return;
+    float *s_coef = s_coef_all + threadIdx.x;
+    softmax_coefs(coefs_raw + (int64_t)g * K, K, s_coef);
+    float mu[3] = {__ldg(fg_means + 3LL * g), __ldg(fg_means + 3LL * g + 1), __ldg(fg_means + 3LL * g + 2)};
+    float4 q4 = __ldg(reinterpret_cast<const float4 *>(fg_quats) + g);
+    float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    for (int n = 0; n < N; ++n) {
+        FramePair f = frame_pair(__ldg(times + n), T);
+        float bp[9], bn[9], bl[9];
+        blend_bases(s_coef, K, T, f.pre, rots, transls, bp);
+        blend_bases(s_coef, K, T, f.nxt, rots, transls, bn);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) bl[j] = (1.0f - f.w) * bp[j] + f.w * bn[j];
+        float om[3], oq[4], oc[3];
+        deform_point<float>(bl, bl + 3, mu, q, om, oq);
+        apply_rt(RTs ? RTs + 12LL * n : nullptr, om, oc);
+        float *mo = out_means + ((int64_t)n * G + g) * 3;
+        mo[0] = oc[0]; mo[1] = oc[1]; mo[2] = oc[2];
+        reinterpret_cast<float4 *>(out_quats)[(int64_t)n * G + g] = make_float4(oq[0], oq[1], oq[2], oq[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+deform_bg_fwd_kernel(const float *__restrict__ bg_means, const float *__restrict__ bg_quats,
+                     const float *__restrict__ RTs, int Gf, int Gb, int G, int N,
+                     float *__restrict__ out_means, float *__restrict__ out_quats) {
+    int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= Gb) return;
+    float mu[3] = {__ldg(bg_means + 3LL * g), __ldg(bg_means + 3LL * g + 1), __ldg(bg_means + 3LL * g + 2)};
+    float4 q = __ldg(reinterpret_cast<const float4 *>(bg_quats) + g);
+    float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+    float4 qh = make_float4(q.x / nrm, q.y / nrm, q.z / nrm, q.w / nrm);
+    for (int n = 0; n < N; ++n) {
+        float oc[3];
+        apply_rt(RTs ? RTs + 12LL * n : nullptr, mu, oc);
+        float *mo = out_means + ((int64_t)n * G + Gf + g) * 3;
+        mo[0] = oc[0]; mo[1] = oc[1]; mo[2] = oc[2];
+        reinterpret_cast<float4 *>(out_quats)[(int64_t)n * G + Gf + g] = qh;
+    }
+}
+
+// ------------------------------------------------------------------------------- backward
+template <int NV>
+__device__ __forceinline__ void warp_transpose_reduce_d(float (&v)[NV], int lane) {
+#pragma unroll
+    for (int h = NV / 2; h >= 1; h >>= 1) {
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float lo = v[i], hi = v[i + h];
+            const float send = upper ? lo : hi;
+            const float keep = upper ? hi : lo;
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+#pragma unroll
+    for (int o = NV; o < 32; o <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+
+// v_out_means'' -> v_mu' = R_rt^T v, and the 12 camera-delta gradient entries (+1 spare slot
+// used by the fg kernel for the time gradient), reduced over the CTA into s_red[16]
+__device__ __forceinline__ void rt_backward(const float *__restrict__ RT, const float vm[3], const float mprime[3],
+                                            float vmu[3], float r16[16]) {
+    if (RT == nullptr) {
+        vmu[0] = vm[0]; vmu[1] = vm[1]; vmu[2] = vm[2];
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) vmu[j] = __ldg(RT + j) * vm[0] + __ldg(RT + 4 + j) * vm[1] + __ldg(RT + 8 + j) * vm[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r16[4 * i + j] = vm[i] * mprime[j];
+        r16[4 * i + 3] = vm[i];
+    }
+}
+
+__global__ void __launch_bounds__(kDefThreads)
+deform_fg_bwd_kernel(const float *__restrict__ fg_means, const float *__restrict__ fg_quats,
+                     const float *__restrict__ coefs_raw, const float *__restrict__ rots,
+                     const float *__restrict__ transls, const float *__restrict__ times,
+                     const float *__restrict__ RTs, int Gf, int G, int K, int T, int N,
+                     const float *__restrict__ v_out_means, const float *__restrict__ v_out_quats,
+                     float *__restrict__ v_fg_means, float *__restrict__ v_fg_quats,
+                     float *__restrict__ v_coefs_raw, float *__restrict__ v_rots,
+                     float *__restrict__ v_transls, float *__restrict__ v_times, float *__restrict__ v_RTs) {
+    extern __shared__ float smem[];
+    float *s_coef_all = smem;                          // [K][kDefThreads] softmaxed coefficients
+    float *s_vcoef_all = smem + K * kDefThreads;       // [K][kDefThreads] dL/dcoef
+    float *s_vB = smem + 2 * K * kDefThreads;          // [K][9]   sum_g c_k * v_blend_j   (current n)
+    float *s_red = s_vB + K * 9;                       // [16]     12 camera entries + time gradient
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = blockIdx.x * kDefThreads + tid;
+    const bool active = g < Gf;
+    float *s_coef = s_coef_all + tid;
+    float *s_vcoef = s_vcoef_all + tid;
+    float mu[3] = {0.f, 0.f, 0.f}, q[4] = {1.f, 0.f, 0.f, 0.f};
+    if (active) {
+        softmax_coefs(coefs_raw + (int64_t)g * K, K, s_coef);
+        mu[0] = __ldg(fg_means + 3LL * g); mu[1] = __ldg(fg_means + 3LL * g + 1); mu[2] = __ldg(fg_means + 3LL * g + 2);
+        float4 q4 = __ldg(reinterpret_cast<const float4 *>(fg_quats) + g);
+        q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+    } else {
+        for (int k = 0; k < K; ++k) s_coef[k * kDefThreads] = 0.f;
+    }
+    for (int k = 0; k < K; ++k) s_vcoef[k * kDefThreads] = 0.f;
+    float v_mu[3] = {0.f, 0.f, 0.f}, v_q[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int n = 0; n < N; ++n) {
+        for (int e = tid; e < K * 9 + 16; e += kDefThreads) s_vB[e] = 0.f;  // s_red follows s_vB
+        __syncthreads();
+        const FramePair f = frame_pair(__ldg(times + n), T);
+        const float *RT = RTs ? RTs + 12LL * n : nullptr;
+        float vb[9];
+        float r16[16];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) vb[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r16[j] = 0.f;
+        if (active) {
+            float bp[9], bn[9], bl[9];
+            blend_bases(s_coef, K, T, f.pre, rots, transls, bp);
+            blend_bases(s_coef, K, T, f.nxt, rots, transls, bn);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) bl[j] = (1.0f - f.w) * bp[j] + f.w * bn[j];
+            const float *vmp = v_out_means + ((int64_t)n * G + g) * 3;
+            const float vm[3] = {__ldg(vmp), __ldg(vmp + 1), __ldg(vmp + 2)};
+            const float4 vq4 = __ldg(reinterpret_cast<const float4 *>(v_out_quats) + (int64_t)n * G + g);
+            const float vq[4] = {vq4.x, vq4.y, vq4.z, vq4.w};
+            // dual evaluation: inputs 0-2 tl, 3-8 r6, 9-11 mu, 12-15 q_raw
+            typedef Dual<16> DU;
+            DU in[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+#pragma unroll
+                for (int b2 = 0; b2 < 16; ++b2) in[a].d[b2] = (a == b2) ? 1.f : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 9; ++j) in[j].v = bl[j];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) in[9 + j].v = mu[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) in[12 + j].v = q[j];
+            DU om[3], oq[4];
+            deform_point<DU>(in, in + 3, in + 9, in + 12, om, oq);
+            const float mprime[3] = {om[0].v, om[1].v, om[2].v};
+            float vmu[3];
+            rt_backward(RT, vm, mprime, vmu, r16);
+            float grad[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a)
+                grad[a] = vmu[0] * om[0].d[a] + vmu[1] * om[1].d[a] + vmu[2] * om[2].d[a] + vq[0] * oq[0].d[a] +
+                          vq[1] * oq[1].d[a] + vq[2] * oq[2].d[a] + vq[3] * oq[3].d[a];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) vb[j] = grad[j];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v_mu[j] += grad[9 + j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v_q[j] += grad[12 + j];
+            // time gradient: d/dw of the lerp
+            float vw = 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) vw += (bn[j] - bp[j]) * vb[j];
+            r16[15] = vw;
+            // dL/dcoef_k += sum_j lerp(base_pre, base_next)[k][j] * vb_j
+            for (int k = 0; k < K; ++k) {
+                const float *tp = transls + ((int64_t)k * T + f.pre) * 3, *tn = transls + ((int64_t)k * T + f.nxt) * 3;
+                const float *rp = rots + ((int64_t)k * T + f.pre) * 6, *rn = rots + ((int64_t)k * T + f.nxt) * 6;
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc += ((1.0f - f.w) * __ldg(tp + j) + f.w * __ldg(tn + j)) * vb[j];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc += ((1.0f - f.w) * __ldg(rp + j) + f.w * __ldg(rn + j)) * vb[3 + j];
+                s_vcoef[k * kDefThreads] += acc;
+            }
+        }
+        // reductions over the Gaussians of this CTA (all lanes participate)
+        warp_transpose_reduce_d<16>(r16, lane);
+        if (lane < 16 && r16[0] != 0.f) atomicAdd(&s_red[lane], r16[0]);
+        for (int k = 0; k < K; ++k) {
+            const float ck = s_coef[k * kDefThreads];
+            float r[16];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) r[j] = ck * vb[j];
+#pragma unroll
+            for (int j = 9; j < 16; ++j) r[j] = 0.f;
+            warp_transpose_reduce_d<16>(r, lane);
+            if (lane < 9 && r[0] != 0.f) atomicAdd(&s_vB[k * 9 + lane], r[0]);
+        }
+        __syncthreads();
+        // flush: bases at pre get (1-w), at next get w
+        for (int e = tid; e < K * 9; e += kDefThreads) {
+            const float val = s_vB[e];
+            if (val == 0.f) continue;
+            const int k = e / 9, jj = e - 9 * k;
+            if (jj < 3) {
+                atomicAdd(v_transls + ((int64_t)k * T + f.pre) * 3 + jj, (1.0f - f.w) * val);
+                atomicAdd(v_transls + ((int64_t)k * T + f.nxt) * 3 + jj, f.w * val);
+            } else {
+                atomicAdd(v_rots + ((int64_t)k * T + f.pre) * 6 + (jj - 3), (1.0f - f.w) * val);
+                atomicAdd(v_rots + ((int64_t)k * T + f.nxt) * 6 + (jj - 3), f.w * val);
+            }
+        }
+        if (tid < 12 && v_RTs && s_red[tid] != 0.f) atomicAdd(v_RTs + 12LL * n + tid, s_red[tid]);
+        if (tid == 15 && s_red[15] != 0.f) atomicAdd(v_times + n, s_red[15]);
+        __syncthreads();
+    }
+    if (active) {
+        v_fg_means[3LL * g] = v_mu[0]; v_fg_means[3LL * g + 1] = v_mu[1]; v_fg_means[3LL * g + 2] = v_mu[2];
+        reinterpret_cast<float4 *>(v_fg_quats)[g] = make_float4(v_q[0], v_q[1], v_q[2], v_q[3]);
+        // softmax backward: v_raw_k = c_k (v_c_k - sum_m c_m v_c_m)
+        float dotp = 0.f;
+        for (int k = 0; k < K; ++k) dotp += s_coef[k * kDefThreads] * s_vcoef[k * kDefThreads];
+        for (int k = 0; k < K; ++k)
+            v_coefs_raw[(int64_t)g * K + k] = s_coef[k * kDefThreads] * (s_vcoef[k * kDefThreads] - dotp);
+    }
+}
+
+__global__ void __launch_bounds__(kDefThreads)
+deform_bg_bwd_kernel(const float *__restrict__ bg_means, const float *__restrict__ bg_quats,
+                     const float *__restrict__ RTs, int Gf, int Gb, int G, int N,
+                     const float *__restrict__ v_out_means, const float *__restrict__ v_out_quats,
+                     float *__restrict__ v_bg_means, float *__restrict__ v_bg_quats, float *__restrict__ v_RTs) {
+    __shared__ float s_red[16];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = blockIdx.x * kDefThreads + tid;
+    const bool active = g < Gb;
+    float mu[3] = {0.f, 0.f, 0.f};
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (active) {
+        mu[0] = __ldg(bg_means + 3LL * g); mu[1] = __ldg(bg_means + 3LL * g + 1); mu[2] = __ldg(bg_means + 3LL * g + 2);
+        q = __ldg(reinterpret_cast<const float4 *>(bg_quats) + g);
+    }
+    float v_mu[3] = {0.f, 0.f, 0.f};
+    float4 vqh = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < N; ++n) {
+        if (tid < 16) s_red[tid] = 0.f;
+        __syncthreads();
+        float r16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r16[j] = 0.f;
+        if (active) {
+            const float *vmp = v_out_means + ((int64_t)n * G + Gf + g) * 3;
+            const float vm[3] = {__ldg(vmp), __ldg(vmp + 1), __ldg(vmp + 2)};
+            float vmu[3];
+            rt_backward(RTs ? RTs + 12LL * n : nullptr, vm, mu, vmu, r16);
+            v_mu[0] += vmu[0]; v_mu[1] += vmu[1]; v_mu[2] += vmu[2];
+            const float4 vq = __ldg(reinterpret_cast<const float4 *>(v_out_quats) + (int64_t)n * G + Gf + g);
+            vqh.x += vq.x; vqh.y += vq.y; vqh.z += vq.z; vqh.w += vq.w;
+        }
+        if (v_RTs && RTs) {
+            warp_transpose_reduce_d<16>(r16, lane);
+            if (lane < 12 && r16[0] != 0.f) atomicAdd(&s_red[lane], r16[0]);
+            __syncthreads();
+            if (tid < 12 && s_red[tid] != 0.f) atomicAdd(v_RTs + 12LL * n + tid, s_red[tid]);
+        }
+        __syncthreads();
+    }
+    if (active) {
+        v_bg_means[3LL * g] = v_mu[0]; v_bg_means[3LL * g + 1] = v_mu[1]; v_bg_means[3LL * g + 2] = v_mu[2];
+        // F.normalize backward: q_hat = q / max(|q|, eps)
+        float nrm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+        float4 out;
+        if (nrm >= 1e-12f) {
+            float inv = 1.0f / nrm;
+            float4 qh = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+            float dotp = vqh.x * qh.x + vqh.y * qh.y + vqh.z * qh.z + vqh.w * qh.w;
+            out = make_float4((vqh.x - dotp * qh.x) * inv, (vqh.y - dotp * qh.y) * inv, (vqh.z - dotp * qh.z) * inv,
+                              (vqh.w - dotp * qh.w) * inv);
+        } else {
+            out = make_float4(vqh.x * 1e12f, vqh.y * 1e12f, vqh.z * 1e12f, vqh.w * 1e12f);
+        }
+        reinterpret_cast<float4 *>(v_bg_quats)[g] = out;
+    }
+}
+
+}  // namespace d4
+
+using namespace d4;
+
+static int check_deform(const char *name, int Gf, int Gb, int K, int T, int N) {
+    D4_CHECK_ARG(Gf >= 0 && Gb >= 0 && N >= 1 && T >= 1, "%s: bad sizes", name);
+    D4_CHECK_ARG(Gf == 0 || (K >= 1 && K <= kMaxK), "%s: K must be in [1,%d]", name, kMaxK);
+    return 0;
+}
+
+extern "C" int d4_deform_fwd(const float *fg_means, const float *fg_quats, const float *motion_coefs,
+                             const float *bg_means, const float *bg_quats, const float *rots,
+                             const float *transls, const float *times, const float *RTs, int Gf, int Gb, int K,
+                             int T, int N, float *out_means, float *out_quats, d4_stream_t stream) {
+    if (int rc = check_deform("d4_deform_fwd", Gf, Gb, K, T, N)) return rc;
+    D4_CHECK_ARG(out_means && out_quats && ((uintptr_t)out_quats & 15) == 0, "d4_deform_fwd: bad outputs");
+    const int G = Gf + Gb;
+    if (Gf > 0) {
+        D4_CHECK_ARG(fg_means && fg_quats && motion_coefs && rots && transls && times && ((uintptr_t)fg_quats & 15) == 0,
+                     "d4_deform_fwd: null/unaligned fg input");
+        size_t smem = sizeof(float) * K * kDefThreads;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(deform_fg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        deform_fg_fwd_kernel<<<cdiv(Gf, kDefThreads), kDefThreads, smem, as_stream(stream)>>>(
+            fg_means, fg_quats, motion_coefs, rots, transls, times, RTs, Gf, G, K, T, N, out_means, out_quats);
+    }
+    if (Gb > 0) {
+        D4_CHECK_ARG(bg_means && bg_quats && ((uintptr_t)bg_quats & 15) == 0, "d4_deform_fwd: null/unaligned bg input");
+        deform_bg_fwd_kernel<<<cdiv(Gb, 256), 256, 0, as_stream(stream)>>>(bg_means, bg_quats, RTs, Gf, Gb, G, N,
+                                                                            out_means, out_quats);
+    }
+    D4_CHECK_LAUNCH("d4_deform_fwd");
+    return 0;
+}
+
+extern "C" int d4_deform_bwd(const float *fg_means, const float *fg_quats, const float *motion_coefs,
+                             const float *bg_means, const float *bg_quats, const float *rots,
+                             const float *transls, const float *times, const float *RTs, int Gf, int Gb, int K,
+                             int T, int N, const float *v_out_means, const float *v_out_quats, float *v_fg_means,
+                             float *v_fg_quats, float *v_motion_coefs, float *v_bg_means, float *v_bg_quats,
+                             float *v_rots, float *v_transls, float *v_times, float *v_RTs, d4_stream_t stream) {
+    if (int rc = check_deform("d4_deform_bwd", Gf, Gb, K, T, N)) return rc;
+    D4_CHECK_ARG(v_out_means && v_out_quats && ((uintptr_t)v_out_quats & 15) == 0, "d4_deform_bwd: bad cotangents");
+    const int G = Gf + Gb;
+    if (Gf > 0) {
+        D4_CHECK_ARG(fg_means && fg_quats && motion_coefs && rots && transls && times && v_fg_means && v_fg_quats &&
+                         v_motion_coefs && v_rots && v_transls && v_times && ((uintptr_t)fg_quats & 15) == 0 &&
+                         ((uintptr_t)v_fg_quats & 15) == 0,
+                     "d4_deform_bwd: null/unaligned fg pointer");
+        size_t smem = sizeof(float) * (2 * K * kDefThreads + K * 9 + 16);
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(deform_fg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        deform_fg_bwd_kernel<<<cdiv(Gf, kDefThreads), kDefThreads, smem, as_stream(stream)>>>(
+            fg_means, fg_quats, motion_coefs, rots, transls, times, RTs, Gf, G, K, T, N, v_out_means, v_out_quats,
+            v_fg_means, v_fg_quats, v_motion_coefs, v_rots, v_transls, v_times, v_RTs);
+    }
+    if (Gb > 0) {
+        D4_CHECK_ARG(bg_means && bg_quats && v_bg_means && v_bg_quats && ((uintptr_t)bg_quats & 15) == 0 &&
+                         ((uintptr_t)v_bg_quats & 15) == 0,
+                     "d4_deform_bwd: null/unaligned bg pointer");
+        deform_bg_bwd_kernel<<<cdiv(Gb, kDefThreads), kDefThreads, 0, as_stream(stream)>>>(
+            bg_means, bg_quats, RTs, Gf, Gb, G, N, v_out_means, v_out_quats, v_bg_means, v_bg_quats, v_RTs);
+    }
+    D4_CHECK_LAUNCH("d4_deform_bwd");
+    return 0;
+}

@@ -1,0 +1,161 @@
+// deform_math.cuh -- per-Gaussian SE(3) deformation arithmetic (SURVEY.md rows
+// a3-a5), written once as a template over the scalar type:
+//   S = float     -> forward kernels
+//   S = Dual<16>  -> backward kernels: forward-mode dual numbers carrying the 16
+//                    partials (blended translation 3, blended rot6d 6, canonical
+//                    mean 3, raw quaternion 4).  Seeding L = <v_out, out> gives
+//                    the exact vector-Jacobian product of the SAME code the
+//                    forward runs, including the branchy rotation-matrix ->
+//                    quaternion conversion, with no hand-derived adjoint to keep
+//                    in sync.
+// Reference arithmetic: F.normalize (eps 1e-12) flow3d/params.py:39;
+// cont_6d_to_rmat flow3d/transforms.py:41-53; R*mu+t and
+// quat(R) (x) q flow3d/scene_model.py:89-102 (roma rotmat_to_unitquat /
+// quat_product, XYZW).
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define D4_HD __host__ __device__ __forceinline__
+#else
+#define D4_HD static inline
+#endif
+
+namespace d4 {
+
+template <int ND>
+struct Dual {
+    float v;
+    float d[ND];
+};
+
+// ---- scalar overloads (float) ---------------------------------------------------
+D4_HD float d_const(float, float c) { return c; }
+D4_HD float d_val(float a) { return a; }
+D4_HD float d_sqrt(float a) { return sqrtf(a); }
+D4_HD float d_max_const(float a, float c) { return a >= c ? a : c; }
+
+// ---- dual overloads ---------------------------------------------------------------
+template <int ND>
+D4_HD Dual<ND> d_const(const Dual<ND> &, float c) {
+    Dual<ND> r;
+    r.v = c;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = 0.f;
+    return r;
+}
+template <int ND>
+D4_HD float d_val(const Dual<ND> &a) { return a.v; }
+template <int ND>
+D4_HD Dual<ND> operator+(const Dual<ND> &a, const Dual<ND> &b) {
+    Dual<ND> r;
+    r.v = a.v + b.v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] + b.d[i];
+    return r;
+}
+template <int ND>
+D4_HD Dual<ND> operator-(const Dual<ND> &a, const Dual<ND> &b) {
+    Dual<ND> r;
+    r.v = a.v - b.v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] - b.d[i];
+    return r;
+}
+template <int ND>
+D4_HD Dual<ND> operator*(const Dual<ND> &a, const Dual<ND> &b) {
+    Dual<ND> r;
+    r.v = a.v * b.v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+    return r;
+}
+template <int ND>
+D4_HD Dual<ND> operator/(const Dual<ND> &a, const Dual<ND> &b) {
+    Dual<ND> r;
+    float inv = 1.0f / b.v;
+    r.v = a.v * inv;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+    return r;
+}
+template <int ND>
+D4_HD Dual<ND> d_sqrt(const Dual<ND> &a) {
+    Dual<ND> r;
+    r.v = sqrtf(a.v);
+    float k = a.v > 0.f ? 0.5f / r.v : 0.f;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = k * a.d[i];
+    return r;
+}
+template <int ND>
+D4_HD Dual<ND> d_max_const(const Dual<ND> &a, float c) { return a.v >= c ? a : d_const(a, c); }
+
+// float arithmetic written through the same spelling as the dual code
+template <typename S>
+D4_HD S d_dot3(const S *a, const S *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// (tl, r6, mu, q_raw[wxyz]) -> (mu' = R mu + tl, q' = normalize(wxyz(quat(R) (x) xyzw(normalize(q_raw)))))
+template <typename S>
+D4_HD void deform_point(const S *tl, const S *r6, const S *mu, const S *qraw, S *om, S *oq) {
+    const float eps = 1e-12f;
+    // q_hat = F.normalize(q_raw)
+    S qn = d_sqrt(qraw[0] * qraw[0] + qraw[1] * qraw[1] + qraw[2] * qraw[2] + qraw[3] * qraw[3]);
+    S qd = d_max_const(qn, eps);
+    S qh[4] = {qraw[0] / qd, qraw[1] / qd, qraw[2] / qd, qraw[3] / qd};
+    // Gram-Schmidt (cont_6d_to_rmat): columns x, y, z
+    S an = d_max_const(d_sqrt(d_dot3(r6, r6)), eps);
+    S x[3] = {r6[0] / an, r6[1] / an, r6[2] / an};
+    S bx = r6[3] * x[0] + r6[4] * x[1] + r6[5] * x[2];
+    S yp[3] = {r6[3] - bx * x[0], r6[4] - bx * x[1], r6[5] - bx * x[2]};
+    S yn = d_max_const(d_sqrt(d_dot3(yp, yp)), eps);
+    S y[3] = {yp[0] / yn, yp[1] / yn, yp[2] / yn};
+    S z[3] = {x[1] * y[2] - x[2] * y[1], x[2] * y[0] - x[0] * y[2], x[0] * y[1] - x[1] * y[0]};
+    // R[i][0] = x[i], R[i][1] = y[i], R[i][2] = z[i]
+#pragma unroll
+    for (int i = 0; i < 3; ++i) om[i] = x[i] * mu[0] + y[i] * mu[1] + z[i] * mu[2] + tl[i];
+    // roma.rotmat_to_unitquat (XYZW), SciPy-style: argmax over (R00, R11, R22, trace)
+    S tr = x[0] + y[1] + z[2];
+    float d0 = d_val(x[0]), d1 = d_val(y[1]), d2 = d_val(z[2]), d3 = d_val(tr);
+    int choice = 0;
+    float best = d0;
+    if (d1 > best) { best = d1; choice = 1; }
+    if (d2 > best) { best = d2; choice = 2; }
+    if (d3 > best) { best = d3; choice = 3; }
+    S one = d_const(tr, 1.0f), two = d_const(tr, 2.0f);
+    S p[4];  // xyzw
+    if (choice == 3) {
+        p[0] = y[2] - z[1];  // R21 - R12
+        p[1] = z[0] - x[2];  // R02 - R20
+        p[2] = x[1] - y[0];  // R10 - R01
+        p[3] = one + tr;
+    } else if (choice == 0) {  // i=0, j=1, k=2
+        p[0] = one - tr + two * x[0];
+        p[1] = x[1] + y[0];  // R10 + R01
+        p[2] = x[2] + z[0];  // R20 + R02
+        p[3] = y[2] - z[1];  // R21 - R12
+    } else if (choice == 1) {  // i=1, j=2, k=0
+        p[1] = one - tr + two * y[1];
+        p[2] = y[2] + z[1];  // R21 + R12
+        p[0] = y[0] + x[1];  // R01 + R10
+        p[3] = z[0] - x[2];  // R02 - R20
+    } else {  // i=2, j=0, k=1
+        p[2] = one - tr + two * z[2];
+        p[0] = z[0] + x[2];  // R02 + R20
+        p[1] = z[1] + y[2];  // R12 + R21
+        p[3] = x[1] - y[0];  // R10 - R01
+    }
+    S pn = d_sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+    p[0] = p[0] / pn; p[1] = p[1] / pn; p[2] = p[2] / pn; p[3] = p[3] / pn;
+    // roma.quat_product(p, q) with q = xyzw(q_hat) = (qh1, qh2, qh3, qh0)
+    const S &qx = qh[1], &qy = qh[2], &qz = qh[3], &qw = qh[0];
+    S vx = p[3] * qx + qw * p[0] + (p[1] * qz - p[2] * qy);
+    S vy = p[3] * qy + qw * p[1] + (p[2] * qx - p[0] * qz);
+    S vz = p[3] * qz + qw * p[2] + (p[0] * qy - p[1] * qx);
+    S w = p[3] * qw - (p[0] * qx + p[1] * qy + p[2] * qz);
+    // xyzw -> wxyz, F.normalize
+    S on = d_max_const(d_sqrt(w * w + vx * vx + vy * vy + vz * vz), eps);
+    oq[0] = w / on; oq[1] = vx / on; oq[2] = vy / on; oq[3] = vz / on;
+}
+
+}  // namespace d4

@@ -1,0 +1,99 @@
+"""Motion-basis deformation ops on top of libd4gs.so.
+
+``deform_subexposures`` replaces, for all N sub-exposures of a frame at once,
+what the reference computes per loop iteration at flow3d/scene_model.py:323-353:
+``GaussianParams`` activations (params.py:39-43), ``MotionBases.compute_transforms``
+(params.py:142-180), ``cont_6d_to_rmat`` (transforms.py:41-53),
+``SceneModel.compute_poses_fg/all`` (scene_model.py:76-120) and the camera
+sub-exposure transform (scene_model.py:352-353).
+
+``compute_poses_all`` / ``compute_poses_fg`` keep the reference's method names
+and ``[G,B,*]`` output layout for its other callers (trainer.py:478,485).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from ._cabi import D4Error, call, ptr, stream_ptr
+
+
+def _c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _Deform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs):
+        if not fg_means.is_cuda:
+            raise D4Error("deform ops need CUDA tensors: there is no CPU fallback")
+        fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs = map(
+            _c, (fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs))
+        Gf = fg_means.shape[0]
+        Gb = 0 if bg_means is None else bg_means.shape[0]
+        K, T = rots.shape[0], rots.shape[1]
+        N = times.shape[0]
+        G = Gf + Gb
+        dev = fg_means.device
+        out_means = torch.empty((N, G, 3), dtype=torch.float32, device=dev)
+        out_quats = torch.empty((N, G, 4), dtype=torch.float32, device=dev)
+        call("d4_deform_fwd", ptr(fg_means), ptr(fg_quats), ptr(motion_coefs), ptr(bg_means), ptr(bg_quats),
+             ptr(rots), ptr(transls), ptr(times), ptr(RTs), Gf, Gb, K, T, N, ptr(out_means), ptr(out_quats),
+             stream_ptr())
+        ctx.save_for_backward(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs)
+        ctx.cfg = (Gf, Gb, K, T, N)
+        return out_means, out_quats
+
+    @staticmethod
+    def backward(ctx, v_means, v_quats):
+        fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs = ctx.saved_tensors
+        Gf, Gb, K, T, N = ctx.cfg
+        dev = fg_means.device
+        G = Gf + Gb
+        v_means = _c(v_means) if v_means is not None else torch.zeros((N, G, 3), device=dev)
+        v_quats = _c(v_quats) if v_quats is not None else torch.zeros((N, G, 4), device=dev)
+        v_fg_means = torch.empty_like(fg_means)
+        v_fg_quats = torch.empty_like(fg_quats)
+        v_coefs = torch.empty_like(motion_coefs)
+        v_bg_means = torch.empty_like(bg_means) if bg_means is not None else None
+        v_bg_quats = torch.empty_like(bg_quats) if bg_quats is not None else None
+        v_rots = torch.zeros_like(rots)
+        v_transls = torch.zeros_like(transls)
+        v_times = torch.zeros_like(times)
+        v_RTs = torch.zeros_like(RTs) if RTs is not None else None
+        call("d4_deform_bwd", ptr(fg_means), ptr(fg_quats), ptr(motion_coefs), ptr(bg_means), ptr(bg_quats),
+             ptr(rots), ptr(transls), ptr(times), ptr(RTs), Gf, Gb, K, T, N, ptr(v_means), ptr(v_quats),
+             ptr(v_fg_means), ptr(v_fg_quats), ptr(v_coefs), ptr(v_bg_means), ptr(v_bg_quats), ptr(v_rots),
+             ptr(v_transls), ptr(v_times), ptr(v_RTs), stream_ptr())
+        return v_fg_means, v_fg_quats, v_coefs, v_bg_means, v_bg_quats, v_rots, v_transls, v_times, v_RTs
+
+
+def deform_subexposures(fg_means: Tensor, fg_quats: Tensor, motion_coefs: Tensor, bg_means: Optional[Tensor],
+                        bg_quats: Optional[Tensor], rots: Tensor, transls: Tensor, times: Tensor,
+                        RTs: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """All N sub-exposures in one launch.
+
+    fg_means [Gf,3], fg_quats [Gf,4] (raw wxyz), motion_coefs [Gf,K] (raw logits),
+    bg_means [Gb,3] / bg_quats [Gb,4] (raw) or None, rots [K,T,6], transls [K,T,3],
+    times [N] (float frame coordinates), RTs [N,3,4] camera deltas or None.
+    Returns means [N,G,3], quats [N,G,4] (unit, wxyz), fg first then bg."""
+    times = times.reshape(-1).to(torch.float32)
+    return _Deform.apply(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs)
+
+
+def compute_poses_fg(fg_means, fg_quats, motion_coefs, rots, transls, ts) -> Tuple[Tensor, Tensor]:
+    """SceneModel.compute_poses_fg (scene_model.py:76-106): ts [B] -> means [Gf,B,3], quats [Gf,B,4]."""
+    m, q = deform_subexposures(fg_means, fg_quats, motion_coefs, None, None, rots, transls, ts, None)
+    return m.permute(1, 0, 2), q.permute(1, 0, 2)
+
+
+def compute_poses_all(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, ts):
+    """SceneModel.compute_poses_all (scene_model.py:108-120): fg (deformed) first, bg (static) after."""
+    m, q = deform_subexposures(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, ts, None)
+    return m.permute(1, 0, 2), q.permute(1, 0, 2)

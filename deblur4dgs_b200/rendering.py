@@ -1,0 +1,362 @@
+"""gsplat-1.1.1-compatible operator surface on top of libd4gs.so.
+
+``rasterization(...)`` is the drop-in for the call at
+``flow3d/scene_model.py:360-373`` (``from gsplat.rendering import
+rasterization``, scene_model.py:5): same keyword names, same returns
+``(render_colors [C,H,W,D], render_alphas [C,H,W,1], meta)``, same autograd
+contract (two autograd Functions with ``meta["means2d"]`` the non-leaf tensor in
+between, so ``meta["means2d"].retain_grad()`` -- scene_model.py:456-459 -- yields
+the screen-space gradient the densifier reads at trainer.py:975).
+
+The lower-level functions mirror gsplat's own op names
+(``fully_fused_projection``, ``isect_tiles``, ``isect_offset_encode``,
+``rasterize_to_pixels``).  Everything runs on the current CUDA stream through
+the C ABI; there is no CPU / eager fallback.
+
+Extension used by the fused sub-exposure path: ``means`` / ``quats`` may be
+``[C,G,3]`` / ``[C,G,4]`` (one deformed copy of the scene per "camera" = per
+sub-exposure) while ``viewmats`` / ``Ks`` hold a single camera.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import call, ptr, stream_ptr
+
+SUPPORTED_D = (1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32, 33)
+CHANNEL_CHUNK = 32
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _cabi.D4Error("deblur4dgs_b200 ops need CUDA tensors: the render path has no CPU fallback")
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _cam_layout(means: Tensor, quats: Tensor, viewmats: Tensor, Ks: Tensor, G: int):
+    """Number of cameras and element strides between cameras (0 = shared)."""
+    C = max(viewmats.shape[0], means.shape[0] if means.dim() == 3 else 1, quats.shape[0] if quats.dim() == 3 else 1)
+    def stride(t, per, batched_dim):
+        if t.dim() == batched_dim:
+            if t.shape[0] == C:
+                return per
+            if t.shape[0] == 1:
+                return 0
+            raise ValueError("camera dimension mismatch")
+        return 0
+    ms = stride(means, G * 3, 3)
+    qs = stride(quats, G * 4, 3)
+    vs = 16 if viewmats.shape[0] == C else (0 if viewmats.shape[0] == 1 else None)
+    ks = 9 if Ks.shape[0] == C else (0 if Ks.shape[0] == 1 else None)
+    if vs is None or ks is None:
+        raise ValueError("viewmats / Ks must have 1 or C cameras")
+    return C, ms, qs, vs, ks
+
+
+# --------------------------------------------------------------------------- #
+# projection (SURVEY rows a8 + a12)
+# --------------------------------------------------------------------------- #
+class _Projection(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+                tile_size):
+        _check_cuda(means, quats, scales, viewmats, Ks)
+        means, quats, scales, viewmats, Ks = map(_f32c, (means, quats, scales, viewmats, Ks))
+        G = scales.shape[0]
+        C, ms, qs, vs, ks = _cam_layout(means, quats, viewmats, Ks, G)
+        dev = means.device
+        tile_w, tile_h = math.ceil(width / tile_size), math.ceil(height / tile_size)
+        radii = torch.empty((C, G), dtype=torch.int32, device=dev)
+        means2d = torch.empty((C, G, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((C, G), dtype=torch.float32, device=dev)
+        conics = torch.empty((C, G, 3), dtype=torch.float32, device=dev)
+        tiles_per_gauss = torch.empty((C, G), dtype=torch.int32, device=dev)
+        call("d4_project_fwd", ptr(means), ms, ptr(quats), qs, ptr(scales), ptr(viewmats), vs, ptr(Ks), ks, C, G,
+             width, height, eps2d, near_plane, far_plane, radius_clip, tile_size, tile_w, tile_h, ptr(radii),
+             ptr(means2d), ptr(depths), ptr(conics), ptr(tiles_per_gauss), stream_ptr())
+        ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii, conics)
+        ctx.cfg = (C, G, ms, qs, vs, ks, width, height, eps2d)
+        ctx.mark_non_differentiable(radii, tiles_per_gauss)
+        return radii, means2d, depths, conics, tiles_per_gauss
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, _v_tpg):
+        means, quats, scales, viewmats, Ks, radii, conics = ctx.saved_tensors
+        C, G, ms, qs, vs, ks, width, height, eps2d = ctx.cfg
+        dev = means.device
+        zeros = lambda t: torch.zeros_like(t) if t is not None else torch.zeros((C, G), device=dev)
+        v_means2d = _f32c(v_means2d) if v_means2d is not None else torch.zeros_like(conics[..., :2]).contiguous()
+        v_depths = _f32c(v_depths) if v_depths is not None else torch.zeros((C, G), device=dev)
+        v_conics = _f32c(v_conics) if v_conics is not None else torch.zeros_like(conics)
+        v_means = torch.zeros_like(means)
+        v_quats = torch.zeros_like(quats)
+        v_scales = torch.zeros_like(scales)
+        want_vm = ctx.needs_input_grad[3]
+        v_vm_full = torch.zeros((C, 4, 4), dtype=torch.float32, device=dev) if want_vm else None
+        call("d4_project_bwd", ptr(means), ms, ptr(quats), qs, ptr(scales), ptr(viewmats), vs, ptr(Ks), ks, C, G,
+             width, height, eps2d, ptr(radii), ptr(conics), ptr(v_means2d), ptr(v_depths), ptr(v_conics),
+             ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_vm_full), stream_ptr())
+        v_viewmats = None
+        if want_vm:
+            v_viewmats = v_vm_full if viewmats.shape[0] == C else v_vm_full.sum(0, keepdim=True)
+        return (v_means, v_quats, v_scales, v_viewmats, None, None, None, None, None, None, None, None)
+
+
+def fully_fused_projection(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
+                           far_plane=1e10, radius_clip=0.0, tile_size=16):
+    """gsplat.fully_fused_projection (packed=False): returns (radii i32 [C,G], means2d [C,G,2],
+    depths [C,G], conics [C,G,3], tiles_per_gauss i32 [C,G])."""
+    return _Projection.apply(means, quats, scales, viewmats, Ks, int(width), int(height), float(eps2d),
+                             float(near_plane), float(far_plane), float(radius_clip), int(tile_size))
+
+
+# --------------------------------------------------------------------------- #
+# tile binning -- integer, not differentiable
+# --------------------------------------------------------------------------- #
+@torch.no_grad()
+def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+                tiles_per_gauss: Optional[Tensor] = None, sort: bool = True):
+    """gsplat.isect_tiles: returns (tiles_per_gauss i32 [C,G], isect_ids i64 [I], flatten_ids i32 [I]),
+    sorted by (camera, tile, depth bits) with a stable radix sort."""
+    _check_cuda(means2d, radii, depths)
+    C, G = radii.shape
+    dev = means2d.device
+    st = stream_ptr()
+    if tiles_per_gauss is None:
+        raise ValueError("tiles_per_gauss comes from fully_fused_projection (fused first pass)")
+    n = C * G
+    ws_bytes = _cabi.lib().d4_scan_workspace_bytes(n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    cum = torch.empty((C, G), dtype=torch.int32, device=dev)
+    total = torch.empty((1,), dtype=torch.int64, device=dev)
+    call("d4_exclusive_scan_i32", ptr(tiles_per_gauss), n, ptr(cum), ptr(total), ptr(ws), ws_bytes, st)
+    n_isects = int(total.item())  # the one device->host sync of the op (as in gsplat)
+    if n_isects >= 2 ** 31:
+        raise _cabi.D4Error("more than 2^31 tile intersections")
+    isect_ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
+    flatten_ids = torch.empty((n_isects,), dtype=torch.int32, device=dev)
+    if n_isects == 0:
+        return tiles_per_gauss, isect_ids, flatten_ids
+    call("d4_isect_emit", ptr(means2d), ptr(radii), ptr(depths), ptr(cum), C, G, tile_size, tile_width,
+         tile_height, ptr(isect_ids), ptr(flatten_ids), st)
+    if sort:
+        tile_n_bits = _cabi.lib().d4_tile_n_bits(tile_width * tile_height)
+        cam_n_bits = int(math.floor(math.log2(C))) + 1
+        isect_ids, flatten_ids = sort_pairs(isect_ids, flatten_ids, 0, 32 + tile_n_bits + cam_n_bits)
+    return tiles_per_gauss, isect_ids, flatten_ids
+
+
+@torch.no_grad()
+def sort_pairs(keys: Tensor, vals: Tensor, begin_bit: int = 0, end_bit: int = 64):
+    """Stable LSD radix sort of (int64 key >= 0, int32 value) pairs on key bits [begin_bit, end_bit)."""
+    _check_cuda(keys, vals)
+    n = keys.shape[0]
+    dev = keys.device
+    keys_b, vals_b = torch.empty_like(keys), torch.empty_like(vals)
+    ws_bytes = _cabi.lib().d4_sort_workspace_bytes(n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    in_b = ctypes.c_int(0)
+    call("d4_sort_pairs_u64", ptr(keys), ptr(vals), ptr(keys_b), ptr(vals_b), n, begin_bit, end_bit, ptr(ws),
+         ws_bytes, ctypes.byref(in_b), stream_ptr())
+    return (keys_b, vals_b) if in_b.value else (keys, vals)
+
+
+@torch.no_grad()
+def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height: int) -> Tensor:
+    """gsplat.isect_offset_encode: offsets i32 [C, tile_height, tile_width]."""
+    offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=isect_ids.device)
+    call("d4_tile_offsets", ptr(isect_ids), isect_ids.shape[0], C, tile_width, tile_height, ptr(offsets), stream_ptr())
+    return offsets
+
+
+# --------------------------------------------------------------------------- #
+# blend (SURVEY rows a10 + a11)
+# --------------------------------------------------------------------------- #
+class _Blend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, flatten_ids, width,
+                height, tile_size, normalize_depth):
+        _check_cuda(means2d, conics, opacities, colors)
+        means2d, conics, opacities, colors = map(_f32c, (means2d, conics, opacities, colors))
+        depths, backgrounds = _f32c(depths), _f32c(backgrounds)
+        C, G = means2d.shape[:2]
+        D0 = colors.shape[-1]
+        ccs = 0 if colors.dim() == 2 else G * D0
+        D = D0 + (1 if depths is not None else 0)
+        dev = means2d.device
+        tile_h, tile_w = isect_offsets.shape[1:]
+        render_colors = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
+        render_alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
+        last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+        acc_depth = torch.empty((C, height, width), dtype=torch.float32, device=dev) if normalize_depth else None
+        n_isects = flatten_ids.shape[0]
+        call("d4_blend_fwd", ptr(means2d), ptr(conics), ptr(opacities), ptr(colors), ccs, ptr(depths),
+             ptr(backgrounds), C, G, D0, width, height, tile_size, tile_w, tile_h, ptr(isect_offsets),
+             ptr(flatten_ids), n_isects, int(normalize_depth), ptr(render_colors), ptr(render_alphas), ptr(last_ids),
+             ptr(acc_depth), stream_ptr())
+        # NOTE: render_colors is NOT saved -- the reference edits it in place (scene_model.py:391-393)
+        ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, flatten_ids,
+                              render_alphas, last_ids, acc_depth)
+        ctx.cfg = (C, G, D0, ccs, width, height, tile_size, tile_w, tile_h, n_isects, int(normalize_depth))
+        return render_colors, render_alphas
+
+    @staticmethod
+    def backward(ctx, v_render_colors, v_render_alphas):
+        (means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, flatten_ids, render_alphas, last_ids,
+         acc_depth) = ctx.saved_tensors
+        C, G, D0, ccs, width, height, tile_size, tile_w, tile_h, n_isects, normalize_depth = ctx.cfg
+        dev = means2d.device
+        D = D0 + (1 if depths is not None else 0)
+        v_rc = _f32c(v_render_colors) if v_render_colors is not None else torch.zeros((C, height, width, D), device=dev)
+        v_ra = _f32c(v_render_alphas) if v_render_alphas is not None else torch.zeros((C, height, width, 1), device=dev)
+        v_means2d = torch.zeros_like(means2d)
+        v_conics = torch.zeros_like(conics)
+        v_colors = torch.zeros_like(colors)
+        v_opacities = torch.zeros_like(opacities)
+        v_depths = torch.zeros_like(depths) if depths is not None else None
+        call("d4_blend_bwd", ptr(means2d), ptr(conics), ptr(opacities), ptr(colors), ccs, ptr(depths),
+             ptr(backgrounds), C, G, D0, width, height, tile_size, tile_w, tile_h, ptr(isect_offsets),
+             ptr(flatten_ids), n_isects, normalize_depth, ptr(render_alphas), ptr(last_ids), ptr(acc_depth),
+             ptr(v_rc), ptr(v_ra), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opacities), ptr(v_depths),
+             stream_ptr())
+        v_backgrounds = None
+        if backgrounds is not None and ctx.needs_input_grad[5]:
+            # as gsplat: sum over pixels of v_colors * (1 - alpha); the depth channel has no background
+            v_backgrounds = (v_rc[..., :D0] * (1.0 - render_alphas)).sum(dim=(1, 2))
+        return (v_means2d, v_conics, v_opacities, v_colors, v_depths, v_backgrounds, None, None, None, None, None, None)
+
+
+def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets,
+                        flatten_ids, backgrounds=None, depths=None, normalize_depth=False):
+    """gsplat.rasterize_to_pixels (packed=False).  ``colors`` is [G,D0] (shared by all
+    cameras) or [C,G,D0]; ``opacities`` [G]; optional ``depths`` [C,G] is blended as one
+    extra (last) channel, normalised to expected depth when ``normalize_depth``."""
+    D = colors.shape[-1] + (1 if depths is not None else 0)
+    if D not in SUPPORTED_D:
+        raise _cabi.D4Error(f"channel count {D} is not built; rasterization() pads/chunks automatically")
+    return _Blend.apply(means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, flatten_ids,
+                        int(image_width), int(image_height), int(tile_size), bool(normalize_depth))
+
+
+# --------------------------------------------------------------------------- #
+# the operator
+# --------------------------------------------------------------------------- #
+def _pad_channels(colors: Tensor, backgrounds: Optional[Tensor], has_depth: bool):
+    D0 = colors.shape[-1]
+    D = D0 + int(has_depth)
+    target = next(d for d in SUPPORTED_D if d >= D)
+    pad = target - D
+    if pad:
+        colors = torch.cat([colors, colors.new_zeros(colors.shape[:-1] + (pad,))], dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, backgrounds.new_zeros(backgrounds.shape[:-1] + (pad,))], dim=-1)
+    return colors, backgrounds, pad
+
+
+def rasterization(
+    means: Tensor,  # [G,3]  (or [C,G,3]: per-camera centres, sub-exposure batch)
+    quats: Tensor,  # [G,4] wxyz, un-normalised allowed (or [C,G,4])
+    scales: Tensor,  # [G,3]
+    opacities: Tensor,  # [G]
+    colors: Tensor,  # [G,D0] or [C,G,D0]
+    viewmats: Tensor,  # [C,4,4]
+    Ks: Tensor,  # [C,3,3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = False,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: str = "classic",
+    channel_chunk: int = CHANNEL_CHUNK,
+    **unsupported,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """Drop-in for ``gsplat.rendering.rasterization`` (gsplat==1.1.1) as called at
+    flow3d/scene_model.py:360-373.  Supports the argument combinations the reference uses
+    (Appendix A of SURVEY.md): packed=False, sh_degree=None, classic mode, RGB / RGB+D / RGB+ED."""
+    if unsupported:
+        raise NotImplementedError(f"unsupported rasterization arguments: {sorted(unsupported)}")
+    if packed or sparse_grad or absgrad or sh_degree is not None or rasterize_mode != "classic":
+        raise NotImplementedError("only packed=False, sparse_grad=False, absgrad=False, sh_degree=None, "
+                                  "rasterize_mode='classic' are built (what Deblur4DGS uses)")
+    if render_mode not in ("RGB", "RGB+D", "RGB+ED", "D", "ED"):
+        raise ValueError(f"render_mode {render_mode!r}")
+    if tile_size != 16:
+        raise NotImplementedError("tile_size 16 only")
+    G = scales.shape[0]
+    assert means.shape[-2:] == (G, 3) and quats.shape[-2:] == (G, 4) and scales.shape == (G, 3)
+    assert opacities.shape == (G,), "opacities must be [G] (flow3d/params.py:76-77)"
+    assert viewmats.shape[-2:] == (4, 4) and Ks.shape[-2:] == (3, 3)
+
+    radii, means2d, depths, conics, tiles_per_gauss = fully_fused_projection(
+        means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size)
+    C = radii.shape[0]
+    tile_width, tile_height = math.ceil(width / tile_size), math.ceil(height / tile_size)
+    _, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
+                                            tiles_per_gauss=tiles_per_gauss)
+    isect_offsets = isect_offset_encode(isect_ids, C, tile_width, tile_height)
+
+    meta = {
+        "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d, "depths": depths,
+        "conics": conics, "opacities": opacities[None].expand(C, -1), "tile_width": tile_width,
+        "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss, "isect_ids": isect_ids,
+        "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width, "height": height,
+        "tile_size": tile_size, "n_cameras": C,
+    }
+
+    with_depth = render_mode in ("RGB+D", "RGB+ED", "D", "ED")
+    normalize = render_mode in ("RGB+ED", "ED")
+    if render_mode in ("D", "ED"):
+        colors = colors.new_zeros(colors.shape[:-1] + (0,))
+        backgrounds = None if backgrounds is None else backgrounds.new_zeros(backgrounds.shape[:-1] + (0,))
+    D0 = colors.shape[-1]
+    blend_depths = depths if with_depth else None
+
+    if D0 + int(with_depth) <= max(SUPPORTED_D) and D0 <= channel_chunk + 1:
+        colors_p, bg_p, pad = _pad_channels(colors, backgrounds, with_depth)
+        rc, render_alphas = rasterize_to_pixels(means2d, conics, colors_p, opacities, width, height, tile_size,
+                                                isect_offsets, flatten_ids, backgrounds=bg_p, depths=blend_depths,
+                                                normalize_depth=normalize)
+        if pad:
+            rc = torch.cat([rc[..., :D0], rc[..., D0 + pad:]], dim=-1)
+        render_colors = rc
+    else:
+        # channel chunking, as gsplat does for > channel_chunk channels
+        chunks, render_alphas = [], None
+        n_chunks = (D0 + channel_chunk - 1) // channel_chunk
+        for i in range(n_chunks):
+            last = i == n_chunks - 1
+            col = colors[..., i * channel_chunk:(i + 1) * channel_chunk]
+            bg = None if backgrounds is None else backgrounds[..., i * channel_chunk:(i + 1) * channel_chunk]
+            dd = blend_depths if last else None
+            col_p, bg_p, pad = _pad_channels(col, bg, dd is not None)
+            rc, ra = rasterize_to_pixels(means2d, conics, col_p, opacities, width, height, tile_size, isect_offsets,
+                                         flatten_ids, backgrounds=bg_p, depths=dd,
+                                         normalize_depth=normalize and last)
+            if pad:
+                rc = torch.cat([rc[..., :col.shape[-1]], rc[..., col.shape[-1] + pad:]], dim=-1)
+            chunks.append(rc)
+            render_alphas = ra if render_alphas is None else render_alphas
+        render_colors = torch.cat(chunks, dim=-1)
+    return render_colors, render_alphas, meta

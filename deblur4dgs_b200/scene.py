@@ -1,0 +1,104 @@
+"""Fused per-frame render: all N sub-exposures of ``SceneModel.render`` in one pass.
+
+``render_subexposures`` replaces the serial Python loop of the reference
+(flow3d/scene_model.py:323-385: per sub-exposure deformation -> camera delta ->
+``rasterization``) and the N-way combine after it (scene_model.py:386-397) by
+
+    1 deformation launch  (all N timestamps; motion.deform_subexposures)
+    1 projection launch   (N x G Gaussians, "C = N cameras" with per-camera centres)
+    1 binning + sort      (keys carry the sub-exposure index in the camera bits)
+    1 blend launch        (N x tiles CTAs)
+    1 combine launch      (mean / max / min over N, each input read once)
+
+with ONE device->host sync (the intersection count) per blurry frame instead of
+N, and identical per-sub-exposure results: every stage is the same arithmetic
+``rasterization`` runs for a single sub-exposure.
+
+Outputs keep what the reference's callers read: the combined image / alpha, the
+per-sub-exposure stack (``exposure_imgs``, trainer.py:601-617), the sharp middle
+image, and per-sub-exposure ``means2d`` / ``radii`` for the densifier
+(scene_model.py:456-461, trainer.py:953-990).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+from ._cabi import call, ptr, stream_ptr
+from .motion import deform_subexposures
+from .rendering import rasterization
+
+
+class _Combine(torch.autograd.Function):
+    """scene_model.py:386-397 -- mean over N, max on the mask channel, min on the depth channel."""
+
+    @staticmethod
+    def forward(ctx, imgs, alphas, max_ch, min_ch, ref_quirk):
+        imgs, alphas = imgs.contiguous(), alphas.contiguous()
+        N = imgs.shape[0]
+        D = imgs.shape[-1]
+        P = imgs[0].numel() // D
+        out_img = torch.empty_like(imgs[0])
+        out_alpha = torch.empty_like(alphas[0])
+        call("d4_combine_fwd", ptr(imgs), ptr(alphas), N, P, D, max_ch, min_ch, int(ref_quirk), ptr(out_img),
+             ptr(out_alpha), stream_ptr())
+        ctx.save_for_backward(imgs if (max_ch >= 0 or min_ch >= 0) else None)
+        ctx.cfg = (N, P, D, max_ch, min_ch, int(ref_quirk), imgs.shape, alphas.shape)
+        return out_img, out_alpha
+
+    @staticmethod
+    def backward(ctx, v_img, v_alpha):
+        (imgs,) = ctx.saved_tensors
+        N, P, D, max_ch, min_ch, ref_quirk, ishape, ashape = ctx.cfg
+        dev = v_img.device if v_img is not None else v_alpha.device
+        v_img = v_img.contiguous() if v_img is not None else torch.zeros(ishape[1:], device=dev)
+        v_alpha = v_alpha.contiguous() if v_alpha is not None else torch.zeros(ashape[1:], device=dev)
+        v_imgs = torch.empty(ishape, dtype=torch.float32, device=dev)
+        v_alphas = torch.empty(ashape, dtype=torch.float32, device=dev)
+        src = imgs if imgs is not None else v_imgs  # unused by the kernel when there is no max/min channel
+        call("d4_combine_bwd", ptr(src), N, P, D, max_ch, min_ch, ref_quirk, ptr(v_img), ptr(v_alpha), ptr(v_imgs),
+             ptr(v_alphas), stream_ptr())
+        return v_imgs, v_alphas, None, None, None
+
+
+def combine_subexposures(imgs: Tensor, alphas: Tensor, max_ch: int = -1, min_ch: int = -1, ref_quirk: bool = True):
+    """imgs [N,...,D], alphas [N,...,1] -> (combined image [...,D], mean alpha [...,1])."""
+    return _Combine.apply(imgs, alphas, int(max_ch), int(min_ch), bool(ref_quirk))
+
+
+def render_subexposures(
+    fg_means: Tensor, fg_quats: Tensor, motion_coefs: Tensor,
+    bg_means: Optional[Tensor], bg_quats: Optional[Tensor],
+    rots: Tensor, transls: Tensor,
+    times: Tensor,  # [N]
+    RTs: Optional[Tensor],  # [N,3,4]
+    scales: Tensor,  # [G,3] activated (exp), fg first
+    opacities: Tensor,  # [G] activated (sigmoid)
+    colors: Tensor,  # [G,D0] per-Gaussian feature vector (rgb | mask | tracks), scene_model.py:205-289
+    w2c: Tensor,  # [1,4,4]
+    K: Tensor,  # [1,3,3]
+    width: int, height: int,
+    backgrounds: Optional[Tensor] = None,  # [1,D0]
+    render_mode: str = "RGB+ED",
+    combine: bool = True,
+    ref_quirk: bool = True,
+) -> Dict[str, Tensor]:
+    N = times.reshape(-1).shape[0]
+    means, quats = deform_subexposures(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs)
+    bg = None if backgrounds is None else backgrounds.expand(N, -1)
+    imgs, alphas, meta = rasterization(means=means, quats=quats, scales=scales, opacities=opacities, colors=colors,
+                                       backgrounds=bg, viewmats=w2c, Ks=K, width=width, height=height, packed=False,
+                                       render_mode=render_mode)
+    out = {"exposure_imgs": imgs[:, None], "exposure_alphas": alphas[:, None], "means2d": meta["means2d"],
+           "radii": meta["radii"], "meta": meta, "means": means, "quats": quats,
+           "pred_sharp_img": imgs[N // 2][None, ..., 0:3]}
+    if combine:
+        D = imgs.shape[-1]
+        if N > 1:
+            img, alpha = combine_subexposures(imgs, alphas, 3 if D > 3 else -1, 16 if D > 16 else -1, ref_quirk)
+            out["img"], out["acc"] = img[None], alpha[None]
+        else:
+            out["img"], out["acc"] = imgs, alphas
+    return out

@@ -1,0 +1,178 @@
+/*
+ * d4gs.h -- C ABI of libd4gs.so: the B200 (sm_100a) implementation of the
+ * Deblur4DGS per-frame render hot path.
+ *
+ * The reference has no native ABI of its own for this path: it calls the
+ * torch-extension API of gsplat==1.1.1 from Python
+ * (flow3d/scene_model.py:5, 360-373) and plain PyTorch ops for the
+ * deformation (flow3d/params.py:142-180, flow3d/scene_model.py:76-120).  Each
+ * entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 / int32 / int64 data laid out
+ *     row-major and contiguous; the library never allocates, frees or keeps
+ *     device memory; workspaces are passed in by the caller (PyTorch tensors);
+ *   - `stream` is a cudaStream_t (CUstream) -- work is only enqueued, never
+ *     synchronised; functions are re-entrant and keep no global mutable state;
+ *   - return 0 on success, non-zero on error; d4_last_error() returns a
+ *     thread-local message; nothing throws across the boundary;
+ *   - "*_cam_stride" = elements between consecutive cameras of a per-camera
+ *     array, or 0 when all cameras share one copy.  A sub-exposure batch of N
+ *     renders is expressed as C = N cameras with per-camera means / quats
+ *     (stride G*3 / G*4) and shared viewmat / K (stride 0);
+ *   - gradient outputs ("v_*") are ACCUMULATED into (atomicAdd) or overwritten
+ *     as documented per function; unless stated the caller zero-fills them.
+ */
+#ifndef D4GS_H_
+#define D4GS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *d4_stream_t; /* cudaStream_t */
+
+#define D4_ABI_VERSION 1
+
+int d4_version(void);
+const char *d4_last_error(void);
+
+/* ---- a8: projection + 2-D covariance ----------------------------------------
+ * replaces gsplat.fully_fused_projection (fwd) as reached from
+ * gsplat.rendering.rasterization, scene_model.py:360-373; fused with the first
+ * pass of gsplat.isect_tiles (tiles_per_gauss).
+ * means [*,G,3], quats [*,G,4] wxyz (normalised inside), scales [G,3],
+ * viewmats [*,4,4], Ks [*,3,3].
+ * out: radii i32 [C,G] (0 = culled), means2d [C,G,2], depths [C,G],
+ *      conics [C,G,3], tiles_per_gauss i32 [C,G] (may be NULL).           */
+int d4_project_fwd(const float *means, int64_t means_cam_stride, const float *quats,
+                   int64_t quats_cam_stride, const float *scales, const float *viewmats,
+                   int64_t viewmat_cam_stride, const float *Ks, int64_t k_cam_stride, int C, int G,
+                   int width, int height, float eps2d, float near_plane, float far_plane,
+                   float radius_clip, int tile_size, int tile_w, int tile_h, int32_t *radii,
+                   float *means2d, float *depths, float *conics, int32_t *tiles_per_gauss,
+                   d4_stream_t stream);
+
+/* ---- a12: projection backward -------------------------------------------------
+ * replaces gsplat.fully_fused_projection backward.  v_means [*,G,3] and
+ * v_quats [*,G,4] use the input strides; v_scales [G,3]; v_viewmats [C,4,4]
+ * may be NULL.  All four are accumulated into: caller zero-fills.            */
+int d4_project_bwd(const float *means, int64_t means_cam_stride, const float *quats,
+                   int64_t quats_cam_stride, const float *scales, const float *viewmats,
+                   int64_t viewmat_cam_stride, const float *Ks, int64_t k_cam_stride, int C, int G,
+                   int width, int height, float eps2d, const int32_t *radii, const float *conics,
+                   const float *v_means2d, const float *v_depths, const float *v_conics,
+                   float *v_means, float *v_quats, float *v_scales, float *v_viewmats,
+                   d4_stream_t stream);
+
+/* ---- a9: tile binning -----------------------------------------------------------
+ * replaces gsplat.isect_tiles (cumsum + second pass), the CUB radix sort inside
+ * it, and gsplat.isect_offset_encode.                                            */
+
+/* exclusive prefix sum of i32 counts; total (i64 device scalar) = sum of all */
+size_t d4_scan_workspace_bytes(int64_t n);
+int d4_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out_exclusive, int64_t *total,
+                          void *workspace, size_t workspace_bytes, d4_stream_t stream);
+
+/* emit isect_ids i64 = (cam << (32+tile_n_bits)) | (tile << 32) | bits(depth)
+ * and flatten_ids i32 = cam*G + g, in (cam, g, tile row-major) order          */
+int d4_tile_n_bits(int n_tiles);
+int d4_isect_emit(const float *means2d, const int32_t *radii, const float *depths,
+                  const int32_t *cum_tiles_exclusive, int C, int G, int tile_size, int tile_w,
+                  int tile_h, int64_t *isect_ids, int32_t *flatten_ids, d4_stream_t stream);
+
+/* stable LSD radix sort of (u64 key, u32 value) pairs on key bits
+ * [begin_bit, end_bit); ping-pongs between the a and b buffers; *result_in_b
+ * (host int) tells where the sorted data ended up.                              */
+size_t d4_sort_workspace_bytes(int64_t n);
+int d4_sort_pairs_u64(uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint32_t *vals_b,
+                      int64_t n, int begin_bit, int end_bit, void *workspace,
+                      size_t workspace_bytes, int *result_in_b, d4_stream_t stream);
+
+/* offsets i32 [C,tile_h,tile_w]: first sorted index of each (camera, tile) */
+int d4_tile_offsets(const int64_t *isect_ids_sorted, int64_t n_isects, int C, int tile_w,
+                    int tile_h, int32_t *offsets, d4_stream_t stream);
+
+/* ---- a10: blend forward -----------------------------------------------------------
+ * replaces gsplat.rasterize_to_pixels (fwd) plus the Python around it in
+ * gsplat.rendering.rasterization: depth appended as an extra colour channel for
+ * "RGB+ED"/"RGB+D" (depths != NULL, background of that channel = 0) and the
+ * expected-depth normalisation depth / max(alpha, 1e-10) (normalize_depth != 0).
+ * means2d [C,G,2], conics [C,G,3], opacities [G], colors [*,G,D0],
+ * backgrounds [C,D0] or NULL.  D = D0 + (depths ? 1 : 0), 1 <= D <= 64.
+ * out: render_colors [C,H,W,D], render_alphas [C,H,W], last_ids i32 [C,H,W],
+ *      acc_depth [C,H,W] (un-normalised depth, only when normalize_depth).     */
+int d4_blend_fwd(const float *means2d, const float *conics, const float *opacities,
+                 const float *colors, int64_t colors_cam_stride, const float *depths,
+                 const float *backgrounds, int C, int G, int D0, int width, int height,
+                 int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets,
+                 const int32_t *flatten_ids, int64_t n_isects, int normalize_depth,
+                 float *render_colors, float *render_alphas, int32_t *last_ids, float *acc_depth,
+                 d4_stream_t stream);
+
+/* ---- a11: blend backward ------------------------------------------------------------
+ * replaces gsplat.rasterize_to_pixels backward (and autograd of the depth
+ * normalisation).  v_means2d [C,G,2], v_conics [C,G,3], v_colors [*,G,D0]
+ * (colors_cam_stride as forward), v_opacities [G], v_depths [C,G] (iff depths):
+ * accumulated with atomics, caller zero-fills.                                   */
+int d4_blend_bwd(const float *means2d, const float *conics, const float *opacities,
+                 const float *colors, int64_t colors_cam_stride, const float *depths,
+                 const float *backgrounds, int C, int G, int D0, int width, int height,
+                 int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets,
+                 const int32_t *flatten_ids, int64_t n_isects, int normalize_depth,
+                 const float *render_alphas, const int32_t *last_ids, const float *acc_depth,
+                 const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
+                 float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
+                 d4_stream_t stream);
+
+/* ---- a1-a6: motion-basis deformation at N sub-exposure timestamps ----------------------
+ * replaces, fused: GaussianParams activations normalize(quats) / softmax(coefs)
+ * (params.py:39-43), MotionBases.compute_transforms (params.py:142-180),
+ * cont_6d_to_rmat (transforms.py:41-53), SceneModel.compute_poses_fg/all
+ * (scene_model.py:76-120) and the camera sub-exposure transform
+ * (scene_model.py:352-353) for all N iterations of the loop at
+ * scene_model.py:323.
+ * fg_means [Gf,3], fg_quats [Gf,4] raw wxyz, motion_coefs [Gf,K] raw logits,
+ * bg_means [Gb,3], bg_quats [Gb,4] raw, rots [K,T,6], transls [K,T,3],
+ * times [N], RTs [N,3,4] (NULL = identity).  K <= 64.
+ * out: means [N,G,3], quats [N,G,4] (wxyz, unit), G = Gf + Gb, fg first.       */
+int d4_deform_fwd(const float *fg_means, const float *fg_quats, const float *motion_coefs,
+                  const float *bg_means, const float *bg_quats, const float *rots,
+                  const float *transls, const float *times, const float *RTs, int Gf, int Gb, int K,
+                  int T, int N, float *out_means, float *out_quats, d4_stream_t stream);
+
+/* backward of d4_deform_fwd.  v_fg_means / v_fg_quats / v_motion_coefs /
+ * v_bg_means / v_bg_quats are overwritten; v_rots [K,T,6], v_transls [K,T,3],
+ * v_times [N], v_RTs [N,3,4] (may be NULL) are accumulated: caller zero-fills. */
+int d4_deform_bwd(const float *fg_means, const float *fg_quats, const float *motion_coefs,
+                  const float *bg_means, const float *bg_quats, const float *rots,
+                  const float *transls, const float *times, const float *RTs, int Gf, int Gb, int K,
+                  int T, int N, const float *v_out_means, const float *v_out_quats,
+                  float *v_fg_means, float *v_fg_quats, float *v_motion_coefs, float *v_bg_means,
+                  float *v_bg_quats, float *v_rots, float *v_transls, float *v_times, float *v_RTs,
+                  d4_stream_t stream);
+
+/* ---- a13: N-way combine of the sub-exposure renders -------------------------------------
+ * replaces the stack/mean/max/min at scene_model.py:386-397: out = mean over N
+ * of every channel, except channel max_ch (if >= 0) = max over N and channel
+ * min_ch (if >= 0) = min over N; out_alpha = mean of alphas.
+ * imgs [N,P,D], alphas [N,P] -> out_img [P,D], out_alpha [P].
+ * ref_quirk != 0 reproduces the reference literally: there the last render's
+ * tensor is overwritten in place by the average BEFORE the max/min are taken
+ * (scene_model.py:391-393), so the extrema run over {r_0..r_{N-2}, mean}
+ * instead of {r_0..r_{N-1}}.
+ * Backward: v_imgs [N,P,D], v_alphas [N,P] overwritten (max/min route the
+ * gradient to the first arg-extremum, as torch.max/min(dim) do).               */
+int d4_combine_fwd(const float *imgs, const float *alphas, int N, int64_t P, int D, int max_ch,
+                   int min_ch, int ref_quirk, float *out_img, float *out_alpha, d4_stream_t stream);
+int d4_combine_bwd(const float *imgs, int N, int64_t P, int D, int max_ch, int min_ch, int ref_quirk,
+                   const float *v_out_img, const float *v_out_alpha, float *v_imgs, float *v_alphas,
+                   d4_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D4GS_H_ */

@@ -525,7 +525,7 @@ ORC_API void orc_blend_fwd(const float *means2d, const float *conics, const floa
                     if (fabsf(alpha - ALPHA_MIN) <= EDGE_REL * ALPHA_MIN * fmaxf(1.f, fabsf(sigma))) e = 1;
                     if (sigma < 0.f || alpha < ALPHA_MIN) continue;
                     float next_T = T * (1.0f - alpha);
-                    if (fabsf(next_T - T_MIN) <= 4.f * EDGE_REL * T_MIN) e = 1;
+                    if (fabsf(next_T - T_MIN) <= 16.f * EDGE_REL * T_MIN) e = 1;
                     if (next_T <= T_MIN) break;
                     float vis = alpha * T;
                     const float *cp = colors + (long)g * D;

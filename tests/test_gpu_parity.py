@@ -1,0 +1,374 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C ABI vs the CPU oracle.
+
+Tolerances (north_star: <= 1e-4 rel fp32, bit-exact tile/bin indices):
+  * integer outputs (radii, tiles_per_gauss, isect_ids, flatten_ids, isect_offsets) and the
+    projection's float outputs' BITS (means2d, depths, conics): exact;
+  * images / alphas: rel_err <= 1e-4 with the SURVEY 8(c) metric
+    max|d| / max(|ref|, 1e-3*max|ref|), on pixels the oracle does not flag as knife-edge
+    (a threshold decision alpha >= 1/255 or T > 1e-4 within 2e-5 relative of flipping; such a
+    pixel may legitimately take the other branch when exp() differs in the last ulps);
+  * gradients: per-Gaussian sums over pixels. Their fp32 conditioning is ~1e-3 element-wise
+    (torch's own fp32 autograd deviates that much from fp64, tests/test_oracle.py), so they are
+    held to 1e-4 of the TENSOR scale (scale_err) and 99.9% of elements to 1e-3 element-wise.
+Every measured error is also appended to gpurun_out/parity_report.jsonl.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from deblur4dgs_b200.synthetic import make_config, make_scene
+from oracle import deform as odef
+from oracle import raster as orc
+from util import golden, golden_files, quat_sign_align, rel_err, scale_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
+
+
+def report(**kw):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    with open(REPORT, "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+def elem_q(got, ref, q=0.999):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = np.abs(ref).max()
+    if scale == 0:
+        return 0.0
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3 * scale)
+    return float(np.quantile(err, q))
+
+
+def T(a, grad=False):
+    t = torch.as_tensor(np.asarray(a)).to(DEV)
+    return t.requires_grad_(True) if grad else t
+
+
+def run_cuda_raster(inp, W, H, mode, grad=True):
+    from deblur4dgs_b200.rendering import rasterization
+    names = ["means", "quats", "scales", "opacities", "colors", "viewmats", "backgrounds"]
+    t = {k: T(inp[k], grad) for k in names}
+    rc, ra, meta = rasterization(means=t["means"], quats=t["quats"], scales=t["scales"], opacities=t["opacities"],
+                                 colors=t["colors"], backgrounds=t["backgrounds"], viewmats=t["viewmats"],
+                                 Ks=T(inp["Ks"]), width=W, height=H, packed=False, render_mode=mode)
+    return t, rc, ra, meta
+
+
+def check_raster_against(name, inp, W, H, mode, ref, tol_img=1e-4, tol_grad=1e-4):
+    """ref: dict with oracle outputs (numpy)."""
+    t, rc, ra, meta = run_cuda_raster(inp, W, H, mode)
+    # ---- bit-exact integer / projection outputs
+    for k in ["radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"]:
+        assert np.array_equal(meta[k].cpu().numpy(), ref[k]), f"{name}: {k} differs"
+    vis = ref["radii"] > 0
+    for k in ["means2d", "depths", "conics"]:
+        a, b = meta[k].detach().cpu().numpy()[vis], ref[k][vis]
+        assert np.array_equal(a.view(np.int32), b.view(np.int32)), f"{name}: {k} bits differ"
+    # ---- images
+    ok = ref["edge"] == 0
+    e_img = rel_err(rc.detach().cpu().numpy()[ok], ref["render_colors"][ok])
+    e_alpha = rel_err(ra.detach().cpu().numpy()[ok], ref["render_alphas"][ok])
+    n_edge = int((~ok).sum())
+    bad_edge = int((np.abs(rc.detach().cpu().numpy()[~ok] - ref["render_colors"][~ok]).max(axis=-1) > 1e-3).sum()) if n_edge else 0
+    report(test=name, kind="image", rel_err_img=e_img, rel_err_alpha=e_alpha, edge_px=n_edge, edge_px_differ=bad_edge,
+           n_px=int(ok.size), n_isects=int(ref["isect_ids"].shape[0]))
+    assert ok.mean() > 0.999
+    assert e_img <= tol_img, f"{name}: image rel err {e_img}"
+    assert e_alpha <= tol_img, f"{name}: alpha rel err {e_alpha}"
+    # ---- gradients
+    meta["means2d"].retain_grad()
+    vc, va = T(ref["v_render_colors"]), T(ref["v_render_alphas"])
+    ((rc * vc).sum() + (ra * va).sum()).backward()
+    got = {k: t[k].grad.cpu().numpy() for k in t}
+    got["means2d"] = meta["means2d"].grad.cpu().numpy()
+    worst = {}
+    for k in ["means", "quats", "scales", "opacities", "colors", "viewmats", "backgrounds", "means2d"]:
+        r = ref["grad_" + k]
+        worst[k] = (scale_err(got[k], r), elem_q(got[k], r))
+    report(test=name, kind="grad", **{k: v for k, v in worst.items()})
+    for k, (se, eq) in worst.items():
+        assert se <= tol_grad, f"{name}: grad {k} scale_err {se}"
+        assert eq <= 1e-3, f"{name}: grad {k} 99.9% element err {eq}"
+
+
+@pytest.mark.parametrize("fname", golden_files("raster_"))
+def test_rasterization_golden_fixtures(fname):
+    g = golden(fname)
+    check_raster_against(fname, g, int(g["width"]), int(g["height"]), str(g["render_mode"]), g)
+
+
+def oracle_ref(inp, W, H, mode, seed=99):
+    rc, ra, meta = orc.rasterization(inp["means"], inp["quats"], inp["scales"], inp["opacities"], inp["colors"],
+                                     inp["viewmats"], inp["Ks"], W, H, backgrounds=inp["backgrounds"], render_mode=mode)
+    g = torch.Generator().manual_seed(seed)
+    vc = torch.randn(rc.shape, generator=g).numpy()
+    va = torch.randn(ra.shape, generator=g).numpy()
+    grads = orc.rasterization_backward(meta, ra, vc, va)
+    ref = dict(render_colors=rc, render_alphas=ra, v_render_colors=vc, v_render_alphas=va,
+               **{k: meta[k] for k in ["radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets",
+                                       "means2d", "depths", "conics", "edge"]})
+    for k, v in grads.items():
+        if v is not None:
+            ref["grad_" + k] = v
+    return ref
+
+
+def scene_inputs(sc, d0, C=1, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    vm = sc.w2c.repeat(C, 1, 1).clone()
+    for c in range(1, C):
+        a = 0.05 * c
+        vm[c, :3, :3] = torch.tensor([[math.cos(a), 0, math.sin(a)], [0, 1, 0], [-math.sin(a), 0, math.cos(a)]])
+        vm[c, :3, 3] = torch.tensor([0.1 * c, -0.05 * c, 0.02 * c])
+    return dict(means=torch.cat([sc.fg_means, sc.bg_means]).numpy(), quats=torch.cat([sc.fg_quats, sc.bg_quats]).numpy(),
+                scales=sc.scales_all().numpy(), opacities=sc.opacities_all().numpy(), colors=sc.colors_all(d0).numpy(),
+                viewmats=vm.numpy(), Ks=sc.K.repeat(C, 1, 1).numpy(), backgrounds=torch.rand(C, d0, generator=g).numpy())
+
+
+def test_rasterization_c1_config():
+    """BASELINE.json configs[0]: 1k random Gaussians, 288x512, N=1, single view -- image parity."""
+    sc = make_config("c1")
+    inp = scene_inputs(sc, 4)
+    check_raster_against("c1", inp, sc.width, sc.height, "RGB+ED", oracle_ref(inp, sc.width, sc.height, "RGB+ED"))
+
+
+@pytest.mark.parametrize("G,W,H,d0,mode,C,scale_mult", [
+    (20000, 512, 288, 16, "RGB+ED", 1, 1.0),   # dynamic pass: D = 17
+    (20000, 500, 277, 4, "RGB+ED", 2, 2.0),    # static pass: D = 5, ragged image edge, 2 cameras
+    (5000, 130, 70, 3, "RGB", 1, 6.0),         # fat Gaussians: long per-tile lists, early termination
+    (3000, 64, 48, 5, "RGB+D", 1, 2.0),        # D = 6
+])
+def test_rasterization_vs_oracle(G, W, H, d0, mode, C, scale_mult):
+    sc = make_scene(G=G, width=W, height=H, K=4, N=1, seed=G + W, scale_mult=scale_mult)
+    inp = scene_inputs(sc, d0, C)
+    check_raster_against(f"G{G}_{W}x{H}_d{d0}_{mode}_C{C}", inp, W, H, mode, oracle_ref(inp, W, H, mode))
+
+
+def test_empty_culled_and_errors():
+    from deblur4dgs_b200._cabi import D4Error
+    from deblur4dgs_b200.rendering import rasterization
+    means = torch.tensor([[0, 0, -5.0], [0.1, 0, -2.0]], device=DEV)
+    quats = torch.tensor([[1.0, 0, 0, 0], [1, 0, 0, 0]], device=DEV)
+    scales = torch.full((2, 3), 0.1, device=DEV)
+    opac = torch.tensor([0.5, 0.5], device=DEV)
+    colors = torch.ones(2, 3, device=DEV)
+    vm = torch.eye(4, device=DEV)[None]
+    K = torch.tensor([[[50.0, 0, 16], [0, 50, 16], [0, 0, 1]]], device=DEV)
+    bg = torch.tensor([[0.2, 0.3, 0.4]], device=DEV)
+    rc, ra, meta = rasterization(means, quats, scales, opac, colors, vm, K, 32, 32, backgrounds=bg)
+    assert meta["isect_ids"].numel() == 0 and int(meta["radii"].abs().sum()) == 0
+    assert torch.allclose(rc, bg[0].expand_as(rc)) and float(ra.abs().max()) == 0
+    # zero Gaussians
+    rc, ra, meta = rasterization(means[:0], quats[:0], scales[:0], opac[:0], colors[:0], vm, K, 32, 32, backgrounds=bg)
+    assert torch.allclose(rc, bg[0].expand_as(rc))
+    with pytest.raises(D4Error):
+        rasterization(means.cpu(), quats.cpu(), scales.cpu(), opac.cpu(), colors.cpu(), vm.cpu(), K.cpu(), 32, 32)
+    with pytest.raises(NotImplementedError):
+        rasterization(means, quats, scales, opac, colors, vm, K, 32, 32, packed=True)
+
+
+def test_reference_caller_contract():
+    """What flow3d does around the op: non-contiguous means (scene_model.py:352-353), in-place edit of
+    the returned image before backward (:391-393), means2d.retain_grad() (:456-459), viewmats grad
+    (validator.py:430-445)."""
+    from deblur4dgs_b200.rendering import rasterization
+    sc = make_scene(G=4000, width=160, height=96, K=4, N=1, seed=5, scale_mult=2.0)
+    inp = scene_inputs(sc, 4)
+    means = T(inp["means"], True)
+    transR = torch.eye(3, device=DEV)
+    m_nc = (transR @ means.permute(1, 0) + torch.zeros(3, 1, device=DEV)).permute(1, 0)
+    assert not m_nc.is_contiguous()
+    vm = T(inp["viewmats"], True)
+    rc, ra, info = rasterization(means=m_nc, quats=T(inp["quats"]), scales=T(inp["scales"]), opacities=T(inp["opacities"]),
+                                 colors=T(inp["colors"]), backgrounds=T(inp["backgrounds"]), viewmats=vm, Ks=T(inp["Ks"]),
+                                 width=160, height=96, packed=False, render_mode="RGB+ED")
+    assert rc.shape == (1, 96, 160, 5) and ra.shape == (1, 96, 160, 1)
+    assert info["radii"].dtype == torch.int32 and info["radii"].shape == (1, 4000)
+    info["means2d"].retain_grad()
+    avg = rc.detach().clone() * 0.5
+    rc[:, :, :, 0:5] = avg  # the reference overwrites the returned tensor in place
+    (rc.sum() + ra.sum()).backward()
+    assert info["means2d"].grad is not None and info["means2d"].grad.shape == (1, 4000, 2)
+    assert means.grad is not None and vm.grad is not None and vm.grad.shape == (1, 4, 4)
+    assert float(vm.grad.abs().sum()) >= 0
+
+
+def test_sort_scan_offsets_units():
+    from deblur4dgs_b200 import _cabi
+    from deblur4dgs_b200._cabi import call, ptr, stream_ptr
+    from deblur4dgs_b200.rendering import isect_offset_encode, sort_pairs
+    g = torch.Generator().manual_seed(0)
+    for n in [1, 2, 31, 2048, 2049, 100003, 1 << 20]:
+        keys = torch.randint(0, 1 << 44, (n,), generator=g, dtype=torch.int64)
+        keys[: n // 3] = keys[: n // 3] & 0xFF  # many duplicates -> stability visible through the values
+        vals = torch.arange(n, dtype=torch.int32)
+        k2, v2 = sort_pairs(keys.to(DEV), vals.to(DEV), 0, 45)
+        ks, order = torch.sort(keys, stable=True)
+        assert torch.equal(k2.cpu(), ks) and torch.equal(v2.cpu().long(), order), n
+    # partial bit range: only bits [8, 20) are ordered, ties keep input order
+    keys = torch.randint(0, 1 << 30, (50000,), generator=g, dtype=torch.int64)
+    k2, v2 = sort_pairs(keys.to(DEV), torch.arange(50000, dtype=torch.int32, device=DEV), 8, 20)
+    sub = (keys >> 8) & 0xFFF
+    _, order = torch.sort(sub, stable=True)
+    assert torch.equal(v2.cpu().long(), order)
+    # scan
+    for n in [1, 5, 2048, 2049, 300000, 3900000]:
+        x = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32).to(DEV)
+        out = torch.empty_like(x)
+        total = torch.zeros(1, dtype=torch.int64, device=DEV)
+        wsb = _cabi.lib().d4_scan_workspace_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        call("d4_exclusive_scan_i32", ptr(x), n, ptr(out), ptr(total), ptr(ws), wsb, stream_ptr())
+        ref = torch.cumsum(x.long(), 0)
+        assert int(total.item()) == int(ref[-1].item())
+        assert torch.equal(out.long(), ref - x.long())
+    # offsets incl. empty tiles at both ends
+    C, tw, th = 3, 7, 5
+    tb = _cabi.lib().d4_tile_n_bits(tw * th)
+    cam = torch.randint(0, C, (4000,), generator=g)
+    tile = torch.randint(3, tw * th - 4, (4000,), generator=g)
+    keys = torch.sort((cam << (32 + tb)) | (tile << 32) | torch.randint(0, 1 << 30, (4000,), generator=g))[0]
+    off = isect_offset_encode(keys.to(DEV), C, tw, th).cpu().reshape(-1)
+    lin = (keys >> (32 + tb)) * (tw * th) + ((keys >> 32) & ((1 << tb) - 1))
+    expect = torch.searchsorted(lin, torch.arange(C * tw * th))
+    assert torch.equal(off.long(), expect)
+
+
+@pytest.mark.parametrize("fname", golden_files("deform_"))
+def test_deform_against_reference_fixtures(fname):
+    """Fixtures are outputs + autograd grads of the reference's own flow3d code (make_golden.py)."""
+    from deblur4dgs_b200.motion import deform_subexposures
+    g = golden(fname)
+    t = {k[3:]: T(v, True) for k, v in g.items() if k.startswith("in_")}
+    M, Q = deform_subexposures(t["fg_means"], t["fg_quats"], t["motion_coefs"], t["bg_means"], t["bg_quats"], t["rots"],
+                               t["transls"], t["times"], t["RTs"])
+    e_m = rel_err(M.detach().cpu().numpy(), g["out_means"])
+    q = Q.detach().cpu().numpy()
+    e_q = rel_err(q, g["out_quats"])
+    assert np.all((q * g["out_quats"]).sum(-1) > 0.999)
+    ((M * T(g["v_out_means"])).sum() + (Q * T(g["v_out_quats"])).sum()).backward()
+    errs = {k: (scale_err(t[k].grad.cpu().numpy(), g["grad_" + k]), elem_q(t[k].grad.cpu().numpy(), g["grad_" + k]))
+            for k in t}
+    report(test=fname, kind="deform", rel_err_means=e_m, rel_err_quats=e_q, **errs)
+    assert e_m <= 1e-4 and e_q <= 1e-4
+    for k, (se, eq) in errs.items():
+        assert se <= 1e-4 and eq <= 1e-3, (k, se, eq)
+
+
+def test_deform_large_vs_oracle_and_wrappers():
+    from deblur4dgs_b200.motion import compute_poses_all, deform_subexposures
+    sc = make_scene(G=60000, width=64, height=48, K=10, N=9, seed=31)
+    s = sc.to(DEV)
+    M, Q = deform_subexposures(s.fg_means, s.fg_quats, s.motion_coefs, s.bg_means, s.bg_quats, s.rots, s.transls,
+                               s.times, s.RTs)
+    Mo, Qo = odef.deform_subexposures(sc.fg_means, sc.fg_quats, sc.motion_coefs, sc.bg_means, sc.bg_quats, sc.rots,
+                                      sc.transls, sc.times, sc.RTs)
+    assert rel_err(M.cpu().numpy(), Mo.numpy()) <= 1e-4
+    assert rel_err(quat_sign_align(Q.cpu().numpy(), Qo.numpy()), Qo.numpy()) <= 1e-4
+    ts = torch.tensor([0.0, 2.5, 7.0, 9.5])
+    m2, q2 = compute_poses_all(s.fg_means, s.fg_quats, s.motion_coefs, s.bg_means, s.bg_quats, s.rots, s.transls,
+                               ts.to(DEV))
+    mo, qo = odef.compute_poses_all(sc.fg_means, sc.fg_quats, sc.motion_coefs, sc.bg_means, sc.bg_quats, sc.rots,
+                                    sc.transls, ts)
+    assert m2.shape == mo.shape and rel_err(m2.cpu().numpy(), mo.numpy()) <= 1e-4
+    assert rel_err(quat_sign_align(q2.cpu().numpy(), qo.numpy()), qo.numpy()) <= 1e-4
+
+
+def test_combine_matches_reference_expression():
+    """scene_model.py:386-397 restated literally in torch (incl. the in-place alias quirk)."""
+    from deblur4dgs_b200.scene import combine_subexposures
+    g = torch.Generator().manual_seed(4)
+    for N, D in [(5, 17), (9, 5), (1, 5), (3, 3)]:
+        imgs = torch.randn(N, 1, 37, 53, D, generator=g).to(DEV).requires_grad_(True)
+        alphas = torch.rand(N, 1, 37, 53, 1, generator=g).to(DEV).requires_grad_(True)
+        # literal reference
+        allc = [imgs[i].clone() for i in range(N)]
+        render_colors = allc[-1]
+        avg = torch.stack(allc, 0).mean(0) if N > 1 else allc[0]
+        render_colors[:, :, :, 0:D] = avg[:, :, :, 0:D]
+        render_colors[:, :, :, 3:4] = torch.stack(allc, 0).max(0)[0][:, :, :, 3:4]
+        render_colors[:, :, :, 16:17] = torch.stack(allc, 0).min(0)[0][:, :, :, 16:17]
+        ref_alpha = torch.stack([alphas[i] for i in range(N)], 0).mean(0)
+        vi, va = torch.randn(render_colors.shape, generator=g).to(DEV), torch.randn(ref_alpha.shape, generator=g).to(DEV)
+        gi_ref, ga_ref = torch.autograd.grad((render_colors * vi).sum() + (ref_alpha * va).sum(), [imgs, alphas])
+        out, oa = combine_subexposures(imgs, alphas, 3 if D > 3 else -1, 16 if D > 16 else -1, ref_quirk=True)
+        assert torch.allclose(out, render_colors, rtol=1e-6, atol=1e-6) and torch.allclose(oa, ref_alpha, rtol=1e-6, atol=1e-6)
+        gi, ga = torch.autograd.grad((out * vi).sum() + (oa * va).sum(), [imgs, alphas])
+        assert torch.allclose(gi, gi_ref, rtol=1e-5, atol=1e-6) and torch.allclose(ga, ga_ref, rtol=1e-5, atol=1e-6)
+
+
+def _subexposure_inputs(sc, d0):
+    s = sc.to(DEV)
+    g = torch.Generator().manual_seed(77)
+    return s, s.scales_all(), s.opacities_all(), s.colors_all(d0), torch.rand(1, d0, generator=g).to(DEV)
+
+
+def test_render_subexposures_equals_loop_of_single_calls():
+    """The batched 'C = N cameras' path must give, per sub-exposure, exactly what N separate
+    rasterization() calls give (the reference's loop), and match the oracle run on the deformed scene."""
+    from deblur4dgs_b200.motion import deform_subexposures
+    from deblur4dgs_b200.rendering import rasterization
+    from deblur4dgs_b200.scene import render_subexposures
+    sc = make_scene(G=30000, width=320, height=192, K=6, N=5, seed=9, scale_mult=1.5)
+    s, scales, opac, colors, bg = _subexposure_inputs(sc, 16)
+    out = render_subexposures(s.fg_means, s.fg_quats, s.motion_coefs, s.bg_means, s.bg_quats, s.rots, s.transls,
+                              s.times, s.RTs, scales, opac, colors, s.w2c, s.K, sc.width, sc.height, backgrounds=bg)
+    M, Q = deform_subexposures(s.fg_means, s.fg_quats, s.motion_coefs, s.bg_means, s.bg_quats, s.rots, s.transls,
+                               s.times, s.RTs)
+    for i in range(sc.N):
+        rc, ra, info = rasterization(means=M[i], quats=Q[i], scales=scales, opacities=opac, colors=colors,
+                                     backgrounds=bg, viewmats=s.w2c, Ks=s.K, width=sc.width, height=sc.height,
+                                     packed=False, render_mode="RGB+ED")
+        assert torch.equal(out["exposure_imgs"][i], rc) and torch.equal(out["exposure_alphas"][i], ra)
+        assert torch.equal(out["radii"][i], info["radii"][0])
+    # oracle on the CUDA-deformed scene, sub-exposure 2
+    i = 2
+    rc_o, ra_o, meta_o = orc.rasterization(M[i].cpu().numpy(), Q[i].cpu().numpy(), scales.cpu().numpy(), opac.cpu().numpy(),
+                                           colors.cpu().numpy(), s.w2c.cpu().numpy(), s.K.cpu().numpy(), sc.width,
+                                           sc.height, backgrounds=bg.cpu().numpy(), render_mode="RGB+ED")
+    ok = meta_o["edge"][0] == 0
+    assert np.array_equal(out["radii"][i].cpu().numpy(), meta_o["radii"][0])
+    assert rel_err(out["exposure_imgs"][i, 0].cpu().numpy()[ok], rc_o[0][ok]) <= 1e-4
+
+
+def test_full_size_c3_properties():
+    """BASELINE.json configs[2] (720x1280, 300k Gaussians, K=10, N=9, D=17) -- too big for the CPU oracle in a
+    test, so size-independent properties: sorted keys, monotone offsets covering all intersections,
+    alpha in [0,1), linearity of the image in the colours, gradient of a linear functional."""
+    from deblur4dgs_b200.scene import render_subexposures
+    sc = make_config("c3")
+    s, scales, opac, colors, _ = _subexposure_inputs(sc, 16)
+    args = (s.fg_means, s.fg_quats, s.motion_coefs, s.bg_means, s.bg_quats, s.rots, s.transls, s.times, s.RTs, scales, opac)
+    kw = dict(w2c=s.w2c, K=s.K, width=sc.width, height=sc.height, backgrounds=None, combine=False)
+    o1 = render_subexposures(*args, colors, **kw)
+    meta = o1["meta"]
+    ids = meta["isect_ids"]
+    assert bool((ids[1:] >= ids[:-1]).all())
+    off = meta["isect_offsets"].reshape(-1).long()
+    assert bool((off[1:] >= off[:-1]).all()) and int(off[0]) == 0 and int(off[-1]) <= ids.numel()
+    assert int(meta["tiles_per_gauss"].sum()) == ids.numel()
+    a = o1["exposure_alphas"]
+    assert float(a.min()) >= 0.0 and float(a.max()) < 1.0
+    c2 = torch.randn_like(colors)
+    o2 = render_subexposures(*args, c2, **kw)
+    o3 = render_subexposures(*args, colors + 2.0 * c2, **kw)
+    lhs = o3["exposure_imgs"][..., :16]
+    rhs = o1["exposure_imgs"][..., :16] + 2.0 * o2["exposure_imgs"][..., :16]
+    assert float((lhs - rhs).abs().max()) <= 1e-4 * float(rhs.abs().max())
+    # depth channel is independent of the colours
+    assert torch.equal(o1["exposure_imgs"][..., 16], o2["exposure_imgs"][..., 16])
+    # d/dcolors of sum(img * w) == render of ... linear functional check via autograd vs finite identity
+    colors_g = colors.clone().requires_grad_(True)
+    o4 = render_subexposures(*args, colors_g, **kw)
+    wgt = torch.randn_like(o4["exposure_imgs"][..., :16])
+    (o4["exposure_imgs"][..., :16] * wgt).sum().backward()
+    lin = (colors_g.grad * c2).sum()
+    direct = (o2["exposure_imgs"][..., :16] * wgt).sum()
+    assert abs(float(lin) - float(direct)) <= 2e-4 * max(1.0, abs(float(direct)))
+    report(test="c3_properties", kind="props", n_isects=int(ids.numel()), lin=float(lin), direct=float(direct))

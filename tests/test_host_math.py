@@ -1,0 +1,108 @@
+"""CPU checks (-m "not gpu") of the product's per-Gaussian arithmetic.
+
+csrc/project_math.cuh and csrc/deform_math.cuh are __host__ __device__; the
+test-only harness tests/host_harness/harness.cpp compiles them with g++ so the
+very arithmetic the CUDA kernels execute is compared with the oracle here,
+where there is no GPU: projection bit-exactly (radii, means2d, depths, conics,
+tiles_per_gauss), projection backward and the dual-number deformation VJP to
+fp32 round-off.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from deblur4dgs_b200.synthetic import make_scene
+from oracle import deform as odef
+from oracle import raster as orc
+from util import quat_sign_align, rel_err, scale_err
+
+HH_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness")
+
+
+@pytest.fixture(scope="module")
+def hh():
+    src, lib = os.path.join(HH_DIR, "harness.cpp"), os.path.join(HH_DIR, "libhh.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", lib, src],
+                   check=True)
+    return ctypes.CDLL(lib)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("seed,scale_mult", [(1, 1.0), (2, 4.0), (3, 0.3)])
+def test_projection_bit_exact_and_backward(hh, seed, scale_mult):
+    W, H, G = 512, 288, 20000
+    sc = make_scene(G=G, width=W, height=H, K=4, N=1, seed=seed, scale_mult=scale_mult)
+    means = torch.cat([sc.fg_means, sc.bg_means]).numpy().copy()
+    means[:50, 2] = -1.0  # behind the camera
+    means[50:100, 2] = 0.005  # in front of the near plane
+    quats = torch.cat([sc.fg_quats, sc.bg_quats]).numpy()
+    scales = sc.scales_all().numpy()
+    V = sc.w2c[0].numpy().copy()
+    a = 0.07
+    V[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+    V[:3, 3] = [0.05, -0.02, 0.1]
+    K = sc.K[0].numpy()
+    radii, m2, dep, con = orc.project_fwd(means, quats, scales, V[None], K[None], W, H)
+    tpg, _, _ = orc.isect_tiles(m2, radii, dep, 16, 32, 18, sort=False)
+    r2 = np.zeros(G, np.int32); m22 = np.zeros((G, 2), np.float32); d2 = np.zeros(G, np.float32)
+    c2 = np.zeros((G, 3), np.float32); t2 = np.zeros(G, np.int32)
+    hh.hh_project_fwd(_p(means), _p(quats), _p(scales), _p(V), _p(K), G, W, H, ctypes.c_float(0.3),
+                      ctypes.c_float(0.01), ctypes.c_float(1e10), ctypes.c_float(0.0), 16, 32, 18, _p(r2), _p(m22),
+                      _p(d2), _p(c2), _p(t2))
+    assert (radii[0] > 0).sum() > 1000 and (radii[0] == 0).sum() > 100
+    assert np.array_equal(r2, radii[0])
+    assert np.array_equal(m22.view(np.int32), m2[0].view(np.int32))
+    assert np.array_equal(d2.view(np.int32), dep[0].view(np.int32))
+    assert np.array_equal(c2.view(np.int32), con[0].view(np.int32))
+    assert np.array_equal(t2, tpg[0])
+    # backward
+    rng = np.random.default_rng(seed)
+    vm2 = rng.standard_normal((1, G, 2)).astype(np.float32)
+    vd = rng.standard_normal((1, G)).astype(np.float32)
+    vc = rng.standard_normal((1, G, 3)).astype(np.float32)
+    om, oq, os_, ov = orc.project_bwd(means, quats, scales, V[None], K[None], W, H, radii, con, vm2, vd, vc)
+    vmeans = np.zeros((G, 3), np.float32); vquats = np.zeros((G, 4), np.float32); vscales = np.zeros((G, 3), np.float32)
+    vview = np.zeros(16, np.float64)
+    hh.hh_project_bwd(_p(means), _p(quats), _p(scales), _p(V), _p(K), G, W, H, _p(radii), _p(con), _p(vm2), _p(vd),
+                      _p(vc), _p(vmeans), _p(vquats), _p(vscales), _p(vview))
+    assert scale_err(vmeans, om) < 1e-6 and scale_err(vquats, oq) < 1e-6 and scale_err(vscales, os_) < 1e-6
+    assert scale_err(vview.reshape(4, 4), ov[0]) < 1e-6
+
+
+def test_deform_point_and_dual_vjp(hh):
+    n = 4000
+    g = torch.Generator().manual_seed(5)
+    bl = torch.randn(n, 9, generator=g)
+    bl[:, 3:] = torch.tensor([1.0, 0, 0, 0, 1.0, 0]) + 0.6 * torch.randn(n, 6, generator=g)  # all 4 quat branches
+    bl[: n // 4, 3:] = torch.randn(n // 4, 6, generator=g)
+    mu = torch.randn(n, 3, generator=g)
+    q = torch.randn(n, 4, generator=g)
+    vm, vq = torch.randn(n, 3, generator=g), torch.randn(n, 4, generator=g)
+    leaves = [x.clone().requires_grad_(True) for x in (bl, mu, q)]
+    R = odef.cont_6d_to_rmat(leaves[0][:, 3:])
+    om_ref = torch.einsum("pij,pj->pi", R, leaves[1]) + leaves[0][:, :3]
+    qh = torch.nn.functional.normalize(leaves[2], dim=-1)
+    oq_ref = odef.roma.quat_xyzw_to_wxyz(odef.roma.quat_product(odef.roma.rotmat_to_unitquat(R),
+                                                                odef.roma.quat_wxyz_to_xyzw(qh)))
+    oq_ref = torch.nn.functional.normalize(oq_ref, dim=-1)
+    om = np.zeros((n, 3), np.float32); oq = np.zeros((n, 4), np.float32)
+    bln, mun, qn = bl.numpy(), mu.numpy(), q.numpy()
+    hh.hh_deform_point(_p(bln), _p(mun), _p(qn), n, _p(om), _p(oq))
+    assert rel_err(om, om_ref.detach().numpy()) < 1e-4
+    assert np.all((oq * oq_ref.detach().numpy()).sum(-1) > 0.999)  # same sign, same branch
+    assert rel_err(oq, oq_ref.detach().numpy()) < 1e-4
+    gb, gm, gq = torch.autograd.grad((om_ref * vm).sum() + (oq_ref * vq).sum(), leaves)
+    grad = np.zeros((n, 16), np.float32)
+    vmn, vqn = vm.numpy(), vq.numpy()
+    hh.hh_deform_point_vjp(_p(bln), _p(mun), _p(qn), _p(vmn), _p(vqn), n, _p(grad))
+    ref = np.concatenate([gb.numpy(), gm.numpy(), gq.numpy()], axis=1)
+    err = np.abs(grad - ref) / (np.abs(ref) + 1e-3 * np.abs(ref).max(axis=1, keepdims=True) + 1e-6)
+    assert np.quantile(err, 0.999) < 1e-3, np.quantile(err, [0.5, 0.99, 0.999, 1.0])
+    assert scale_err(grad, ref) < 1e-4
