@@ -419,9 +419,9 @@ static int check_blend_args(const char *name, const BlendArgs &a, int tile_size)
     D4_CHECK_ARG(a.C >= 1 && a.G >= 0 && a.D0 >= 0 && a.width > 0 && a.height > 0, "%s: bad sizes", name);
     D4_CHECK_ARG(a.tile_w == (a.width + kTile - 1) / kTile && a.tile_h == (a.height + kTile - 1) / kTile,
                  "%s: tile grid does not match the image size", name);
-    D4_CHECK_ARG(a.means2d && a.conics && a.opacities && a.tile_offsets && (a.flatten_ids || a.n_isects == 0),
-                 "%s: null pointer", name);
-    D4_CHECK_ARG(a.colors || a.D0 == 0, "%s: null colors", name);
+    D4_CHECK_ARG(a.tile_offsets && (a.flatten_ids || a.n_isects == 0), "%s: null pointer", name);
+    D4_CHECK_ARG(a.n_isects == 0 || (a.means2d && a.conics && a.opacities && (a.colors || a.D0 == 0)),
+                 "%s: null Gaussian arrays with a non-empty intersection list", name);
     D4_CHECK_ARG(((uintptr_t)a.means2d & 7) == 0, "%s: means2d must be 8-byte aligned", name);
     if ((a.D0 & 3) == 0 && a.D0 > 0)
         D4_CHECK_ARG(((uintptr_t)a.colors & 15) == 0 && (a.colors_cs & 3) == 0, "%s: colors must be 16-byte aligned", name);

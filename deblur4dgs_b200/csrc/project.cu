@@ -193,6 +193,7 @@ extern "C" int d4_project_fwd(const float *means, int64_t means_cam_stride, cons
                               int32_t *radii, float *means2d, float *depths, float *conics,
                               int32_t *tiles_per_gauss, d4_stream_t stream) {
     D4_CHECK_ARG(C >= 1 && G >= 0 && width > 0 && height > 0 && tile_size > 0, "d4_project_fwd: bad sizes");
+    if (G == 0) return 0;
     D4_CHECK_ARG(means && quats && scales && viewmats && Ks && radii && means2d && depths && conics,
                  "d4_project_fwd: null pointer");
     D4_CHECK_ARG(((uintptr_t)quats & 15) == 0 && ((uintptr_t)means2d & 7) == 0 && (quats_cam_stride % 4) == 0,
@@ -216,6 +217,7 @@ extern "C" int d4_project_bwd(const float *means, int64_t means_cam_stride, cons
                               float *v_viewmats, d4_stream_t stream) {
     (void)eps2d;
     D4_CHECK_ARG(C >= 1 && C <= 65535 && G >= 0, "d4_project_bwd: bad sizes");
+    if (G == 0) return 0;
     D4_CHECK_ARG(means && quats && scales && viewmats && Ks && radii && conics && v_means2d && v_depths &&
                      v_conics && v_means && v_quats && v_scales,
                  "d4_project_bwd: null pointer");
@@ -235,8 +237,8 @@ extern "C" int d4_project_bwd(const float *means, int64_t means_cam_stride, cons
 extern "C" int d4_isect_emit(const float *means2d, const int32_t *radii, const float *depths,
                              const int32_t *cum_tiles_exclusive, int C, int G, int tile_size, int tile_w,
                              int tile_h, int64_t *isect_ids, int32_t *flatten_ids, d4_stream_t stream) {
-    D4_CHECK_ARG(means2d && radii && depths && cum_tiles_exclusive, "d4_isect_emit: null pointer");
     if ((int64_t)C * G == 0) return 0;
+    D4_CHECK_ARG(means2d && radii && depths && cum_tiles_exclusive, "d4_isect_emit: null pointer");
     int tb = d4_tile_n_bits(tile_w * tile_h);
     isect_emit_kernel<<<cdiv((int64_t)C * G, kProjThreads), kProjThreads, 0, as_stream(stream)>>>(
         means2d, radii, depths, cum_tiles_exclusive, C, G, tile_size, tile_w, tile_h, tb, isect_ids,

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/parity_report.jsonl
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== pytest -m gpu" 
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
 echo "== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
 echo "== bench"
