@@ -52,19 +52,63 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
     ly = (w >> 1) * 4 + (lane >> 3);
 }
 
-// stage one batch: thread tr loads Gaussian `idx` (if in range) into slot tr
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kLog2_255 = 7.994353436858858f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Stage one batch: thread tr loads Gaussian `idx` (if in range) into slot tr.
+// Shared-memory record per Gaussian (exponent pre-scaled to base 2 so that the per-pair
+// evaluation is 5 FMA-pipe ops + one MUFU.EX2):
+//   s_geom  = (x, y, L = log2(opacity), flatten id)
+//   s_conic = (A', B', C', 1/opacity)  with  A' = -a/2 log2e, B' = -b log2e, C' = -c/2 log2e
+//   => opacity * exp(-sigma) = exp2(L + A' dx^2 + B' dx dy + C' dy^2)
+//   s_mask  = bit w set iff the Gaussian can reach alpha >= 1/255 on some pixel of warp w's 8x4
+//             block: the ellipse {sigma <= ln(255 o)} has the bounding box
+//             |dx| <= sqrt(2 tau cov_xx), |dy| <= sqrt(2 tau cov_yy); the test is conservative
+//             (slack for rounding), so skipping never changes a result.
 template <int D>
 __device__ __forceinline__ void stage_gaussian(const BlendArgs &a, int c, int64_t idx, bool in_range, int tr,
-                                               float4 *s_geom, float4 *s_conic, float *s_col) {
+                                               int tile_x0, int tile_y0, float4 *s_geom, float4 *s_conic,
+                                               float *s_col, uint32_t *s_mask) {
     constexpr int DS = BlendCfg<D>::DS;
-    if (!in_range) return;
+    if (!in_range) {
+        s_mask[tr] = 0u;
+        return;
+    }
     int32_t g = __ldg(a.flatten_ids + idx);
     int32_t gl = g - c * a.G;
     float2 xy = __ldg(reinterpret_cast<const float2 *>(a.means2d) + g);
     float opac = __ldg(a.opacities + gl);
-    s_geom[tr] = make_float4(xy.x, xy.y, opac, __int_as_float(g));
     const float *cp = a.conics + 3LL * g;
-    s_conic[tr] = make_float4(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), 0.f);
+    const float ca = __ldg(cp), cb = __ldg(cp + 1), cc = __ldg(cp + 2);
+    const float L = __log2f(opac);
+    s_geom[tr] = make_float4(xy.x, xy.y, L, __int_as_float(g));
+    s_conic[tr] = make_float4(-0.5f * kLog2e * ca, -kLog2e * cb, -0.5f * kLog2e * cc, 1.0f / opac);
+    // per-warp reach mask
+    uint32_t mask = 0u;
+    const float tau = (L + kLog2_255) * kLn2;  // ln(255 * opacity)
+    const float det = ca * cc - cb * cb;
+    if (!(det > 0.f) || !(ca > 0.f) || !(cc > 0.f)) {
+        mask = 0xffu;  // degenerate conic: no culling
+    } else if (tau >= 0.f) {
+        const float k = 2.0f * tau / det;
+        const float ex = sqrtf(k * cc) * 1.0001f + 1e-3f;
+        const float ey = sqrtf(k * ca) * 1.0001f + 1e-3f;
+        const float rx = xy.x - (float)tile_x0, ry = xy.y - (float)tile_y0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float x0 = (float)((w & 1) * 8) + 0.5f, y0 = (float)((w >> 1) * 4) + 0.5f;
+            const bool hit = (rx >= x0 - ex) && (rx <= x0 + 7.0f + ex) && (ry >= y0 - ey) && (ry <= y0 + 3.0f + ey);
+            mask |= hit ? (1u << w) : 0u;
+        }
+    }
+    s_mask[tr] = mask;
     const float *col = a.colors + c * a.colors_cs + (int64_t)gl * a.D0;
     float *dst = s_col + tr * DS;
     const int d0 = a.depths ? D - 1 : D;
@@ -94,13 +138,14 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
     __shared__ float4 s_geom[kBatch];
     __shared__ float4 s_conic[kBatch];
     __shared__ __align__(16) float s_col[kBatch * (DS > DP ? DS : DP)];
+    __shared__ uint32_t s_mask[kBatch];
 
     const int n_tiles = a.tile_w * a.tile_h;
     const int ct = blockIdx.x;
     const int c = ct / n_tiles;
     const int tile = ct - c * n_tiles;
     const int ty = tile / a.tile_w, tx = tile - ty * a.tile_w;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
     const int j = tx * kTile + lx, i = ty * kTile + ly;
@@ -122,39 +167,49 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
     for (int b = 0; b < num_batches; ++b) {
         if (__syncthreads_count(done) >= kBlendThreads) break;
         const int64_t batch_start = range_start + (int64_t)kBatch * b;
-        stage_gaussian<D>(a, c, batch_start + tid, batch_start + tid < range_end, tid, s_geom, s_conic, s_col);
+        stage_gaussian<D>(a, c, batch_start + tid, batch_start + tid < range_end, tid, tx * kTile, ty * kTile, s_geom,
+                          s_conic, s_col, s_mask);
         __syncthreads();
         const int batch_size = (int)min((int64_t)kBatch, range_end - batch_start);
-        for (int t = 0; t < batch_size; ++t) {
-            const float4 g0 = s_geom[t];
-            const float4 cn = s_conic[t];
-            const float dx = g0.x - px, dy = g0.y - py;
-            const float sigma = 0.5f * (cn.x * dx * dx + cn.z * dy * dy) + cn.y * dx * dy;
-            const float alpha = fminf(kAlphaMax, g0.z * __expf(-sigma));
-            const bool valid = !done && sigma >= 0.f && alpha >= kAlphaMin;
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            if (valid) {
-                const float next_T = T * (1.0f - alpha);
-                if (next_T <= kTMin) {
-                    done = true;
-                } else {
-                    const float vis = alpha * T;
-                    const float *cp = s_col + t * DS;
+        bool warp_done = __all_sync(0xffffffffu, done);
+        for (int chunk = 0; chunk * 32 < batch_size && !warp_done; ++chunk) {
+            uint32_t bits = __ballot_sync(0xffffffffu, (s_mask[chunk * 32 + lane] >> w) & 1u);
+            while (bits) {
+                const int t = chunk * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 g0 = s_geom[t];
+                const float4 cn = s_conic[t];
+                const float dx = g0.x - px, dy = g0.y - py;
+                const float power = fmaf(cn.z * dy, dy, fmaf(fmaf(cn.y, dy, cn.x * dx), dx, g0.z));
+                const float alpha = fminf(kAlphaMax, ex2_approx(power));
+                const bool valid = !done && power <= g0.z && alpha >= kAlphaMin;
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                if (valid) {
+                    const float next_T = T * (1.0f - alpha);
+                    if (next_T <= kTMin) {
+                        done = true;
+                    } else {
+                        const float vis = alpha * T;
+                        const float *cp = s_col + t * DS;
 #pragma unroll
-                    for (int k4 = 0; k4 < D / 4; ++k4) {
-                        const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
-                        out[4 * k4 + 0] = fmaf(cv.x, vis, out[4 * k4 + 0]);
-                        out[4 * k4 + 1] = fmaf(cv.y, vis, out[4 * k4 + 1]);
-                        out[4 * k4 + 2] = fmaf(cv.z, vis, out[4 * k4 + 2]);
-                        out[4 * k4 + 3] = fmaf(cv.w, vis, out[4 * k4 + 3]);
+                        for (int k4 = 0; k4 < D / 4; ++k4) {
+                            const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
+                            out[4 * k4 + 0] = fmaf(cv.x, vis, out[4 * k4 + 0]);
+                            out[4 * k4 + 1] = fmaf(cv.y, vis, out[4 * k4 + 1]);
+                            out[4 * k4 + 2] = fmaf(cv.z, vis, out[4 * k4 + 2]);
+                            out[4 * k4 + 3] = fmaf(cv.w, vis, out[4 * k4 + 3]);
+                        }
+#pragma unroll
+                        for (int k = D / 4 * 4; k < D; ++k) out[k] = fmaf(cp[k], vis, out[k]);
+                        cur_idx = (int32_t)(batch_start + t);
+                        T = next_T;
                     }
-#pragma unroll
-                    for (int k = D / 4 * 4; k < D; ++k) out[k] = fmaf(cp[k], vis, out[k]);
-                    cur_idx = (int32_t)(batch_start + t);
-                    T = next_T;
+                }
+                if (__all_sync(0xffffffffu, done)) {
+                    warp_done = true;
+                    break;
                 }
             }
-            if (__all_sync(0xffffffffu, done)) break;
         }
     }
 
@@ -231,6 +286,7 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
     float *s_col = reinterpret_cast<float *>(s_conic + kBatch);
     float *s_acc = s_col + kBatch * DS;
     __shared__ int32_t s_max[kBlendThreads / 32];
+    __shared__ uint32_t s_mask[kBatch];
 
     const int n_tiles = a.tile_w * a.tile_h;
     const int ct = blockIdx.x;
@@ -301,68 +357,90 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
         __syncthreads();  // previous batch fully consumed (s_* reuse) and flushed
         const int64_t batch_end = range_end - 1 - (int64_t)kBatch * b;  // slot 0 = furthest back
         const int batch_size = (int)min((int64_t)kBatch, batch_end + 1 - range_start);
-        stage_gaussian<D>(a, c, batch_end - tid, batch_end - tid >= range_start, tid, s_geom, s_conic, s_col);
+        stage_gaussian<D>(a, c, batch_end - tid, batch_end - tid >= range_start, tid, tx * kTile, ty * kTile, s_geom,
+                          s_conic, s_col, s_mask);
         for (int e = tid; e < kBatch * VS; e += kBlendThreads) s_acc[e] = 0.f;
         __syncthreads();
 
-        int t0 = (int)max((int64_t)0, batch_end - (int64_t)warp_bin_final);
-        for (int t = t0; t < batch_size; ++t) {
-            const float4 g0 = s_geom[t];
-            const float4 cn = s_conic[t];
-            const float dx = g0.x - px, dy = g0.y - py;
-            const float sigma = 0.5f * (cn.x * dx * dx + cn.z * dy * dy) + cn.y * dx * dy;
-            const float vis = __expf(-sigma);
-            const float alpha = fminf(kAlphaMax, g0.z * vis);
-            const bool valid = (batch_end - t <= (int64_t)bin_final) && sigma >= 0.f && alpha >= kAlphaMin;
-            if (!__any_sync(0xffffffffu, valid)) continue;
+        const int t0 = (int)max((int64_t)0, batch_end - (int64_t)warp_bin_final);
+        for (int chunk = t0 >> 5; chunk * 32 < batch_size; ++chunk) {
+            uint32_t bits = __ballot_sync(0xffffffffu, (s_mask[chunk * 32 + lane] >> w) & 1u);
+            if (chunk == (t0 >> 5)) bits &= ~((1u << (t0 & 31)) - 1u);  // slots behind the warp's last contributor
+            while (bits) {
+                const int t = chunk * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 g0 = s_geom[t];
+                const float4 cn = s_conic[t];
+                const float dx = g0.x - px, dy = g0.y - py;
+                const float power = fmaf(cn.z * dy, dy, fmaf(fmaf(cn.y, dy, cn.x * dx), dx, g0.z));
+                const float araw = ex2_approx(power);  // opacity * exp(-sigma)
+                const float alpha = fminf(kAlphaMax, araw);
+                const bool valid = (batch_end - t <= (int64_t)bin_final) && power <= g0.z && alpha >= kAlphaMin;
+                if (!__any_sync(0xffffffffu, valid)) continue;
 
-            float r[RN];
+                float r[RN];
 #pragma unroll
-            for (int k = 0; k < RN; ++k) r[k] = 0.f;
-            if (valid) {
-                const float ra = 1.0f / (1.0f - alpha);
-                T *= ra;
-                const float fac = alpha * T;
-                const float *cp = s_col + t * DS;
-                float s = 0.f;
+                for (int k = 0; k < RN; ++k) r[k] = 0.f;
+                if (valid) {
+                    const float ra = __fdividef(1.0f, 1.0f - alpha);  // alpha <= 0.999: MUFU.RCP is within 1 ulp here
+                    T *= ra;
+                    const float fac = alpha * T;
+                    const float *cp = s_col + t * DS;
+                    float s = 0.f;
 #pragma unroll
-                for (int k4 = 0; k4 < D / 4; ++k4) {
-                    const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
-                    s = fmaf(cv.x, v_out[4 * k4 + 0], s);
-                    s = fmaf(cv.y, v_out[4 * k4 + 1], s);
-                    s = fmaf(cv.z, v_out[4 * k4 + 2], s);
-                    s = fmaf(cv.w, v_out[4 * k4 + 3], s);
+                    for (int k4 = 0; k4 < D / 4; ++k4) {
+                        const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
+                        s = fmaf(cv.x, v_out[4 * k4 + 0], s);
+                        s = fmaf(cv.y, v_out[4 * k4 + 1], s);
+                        s = fmaf(cv.z, v_out[4 * k4 + 2], s);
+                        s = fmaf(cv.w, v_out[4 * k4 + 3], s);
+                    }
+#pragma unroll
+                    for (int k = D / 4 * 4; k < D; ++k) s = fmaf(cp[k], v_out[k], s);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) r[k] = fac * v_out[k];
+                    const float v_alpha = s * T - (S - tail) * ra;
+                    S = fmaf(s, fac, S);
+                    if (araw <= kAlphaMax) {
+                        // v_sigma = -araw * v_alpha; conic terms in the primed (base-2) scale:
+                        //   a dx + b dy = -(2 A' dx + B' dy) / log2e
+                        const float v_sigma = -araw * v_alpha;
+                        const float vs2 = v_sigma * (-1.0f / kLog2e);
+                        r[D + 0] = 0.5f * v_sigma * dx * dx;
+                        r[D + 1] = v_sigma * dx * dy;
+                        r[D + 2] = 0.5f * v_sigma * dy * dy;
+                        r[D + 3] = vs2 * fmaf(2.0f * cn.x, dx, cn.y * dy);
+                        r[D + 4] = vs2 * fmaf(cn.y, dx, 2.0f * cn.z * dy);
+                        r[D + 5] = araw * cn.w * v_alpha;  // exp(-sigma) * v_alpha
+                    }
                 }
+                // warp reduction of the V partial sums, then CTA-level accumulation
+                if constexpr (V > 16 && V <= 24) {
+                    // 16 + 8 split: 16 + 9 shuffles instead of 31 for the padded 32-wide butterfly
+                    float ra16[16], rb8[8];
 #pragma unroll
-                for (int k = D / 4 * 4; k < D; ++k) s = fmaf(cp[k], v_out[k], s);
+                    for (int k = 0; k < 16; ++k) ra16[k] = r[k];
 #pragma unroll
-                for (int k = 0; k < D; ++k) r[k] = fac * v_out[k];
-                const float v_alpha = s * T - (S - tail) * ra;
-                S = fmaf(s, fac, S);
-                if (g0.z * vis <= kAlphaMax) {
-                    const float v_sigma = -g0.z * vis * v_alpha;
-                    r[D + 0] = 0.5f * v_sigma * dx * dx;
-                    r[D + 1] = v_sigma * dx * dy;
-                    r[D + 2] = 0.5f * v_sigma * dy * dy;
-                    r[D + 3] = v_sigma * (cn.x * dx + cn.y * dy);
-                    r[D + 4] = v_sigma * (cn.y * dx + cn.z * dy);
-                    r[D + 5] = vis * v_alpha;
-                }
-            }
-            // warp reduction of the V partial sums, then CTA-level accumulation
-            if constexpr (NCHUNK == 1) {
-                warp_transpose_reduce<RN>(r, lane);
-                const int slot = lane & (RW - 1);
-                if (lane < RW && slot < V) atomicAdd(&s_acc[t * VS + slot], r[0]);
-            } else {
+                    for (int k = 0; k < 8; ++k) rb8[k] = r[16 + k];
+                    warp_transpose_reduce<16>(ra16, lane);
+                    warp_transpose_reduce<8>(rb8, lane);
+                    // lanes 0-15 own values 0-15, lanes 16-23 own values 16-23
+                    const float mine = lane < 16 ? ra16[0] : rb8[0];
+                    if (lane < V) atomicAdd(&s_acc[t * VS + lane], mine);
+                } else if constexpr (NCHUNK == 1) {
+                    warp_transpose_reduce<RN>(r, lane);
+                    const int slot = lane & (RW - 1);
+                    if (lane < RW && slot < V) atomicAdd(&s_acc[t * VS + slot], r[0]);
+                } else {
 #pragma unroll
-                for (int ch = 0; ch < NCHUNK; ++ch) {
-                    float rr[32];
+                    for (int ch = 0; ch < NCHUNK; ++ch) {
+                        float rr[32];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) rr[k] = r[ch * 32 + k];
-                    warp_transpose_reduce<32>(rr, lane);
-                    const int slot = ch * 32 + lane;
-                    if (slot < V) atomicAdd(&s_acc[t * VS + slot], rr[0]);
+                        for (int k = 0; k < 32; ++k) rr[k] = r[ch * 32 + k];
+                        warp_transpose_reduce<32>(rr, lane);
+                        const int slot = ch * 32 + lane;
+                        if (slot < V) atomicAdd(&s_acc[t * VS + slot], rr[0]);
+                    }
                 }
             }
         }
