@@ -155,6 +155,16 @@ int d4_deform_bwd(const float *fg_means, const float *fg_quats, const float *mot
                   float *v_bg_quats, float *v_rots, float *v_transls, float *v_times, float *v_RTs,
                   d4_stream_t stream);
 
+/* ---- a7: camera sub-exposure pose interpolation ---------------------------------------------
+ * replaces MoveModel.forward_start_end_mid's pose part (move_model.py:143-147: pp.se3().Exp(),
+ * _interpolate -> spline_utils.linear_interpolation :371-408, .Log(), se3_to_SE3 :204-215).
+ * start6 / end6: the two se(3) 6-vectors [rho, phi] emitted by the MoveModel heads (device
+ * pointers); u_i = linspace(0,1,N)[i].  RTs [N,3,4].  Backward accumulates into v_start6 /
+ * v_end6 [6] (caller zero-fills).                                                              */
+int d4_camera_interp_fwd(const float *start6, const float *end6, int N, float *RTs, d4_stream_t stream);
+int d4_camera_interp_bwd(const float *start6, const float *end6, int N, const float *v_RTs, float *v_start6,
+                         float *v_end6, d4_stream_t stream);
+
 /* ---- a13: N-way combine of the sub-exposure renders -------------------------------------
  * replaces the stack/mean/max/min at scene_model.py:386-397: out = mean over N
  * of every channel, except channel max_ch (if >= 0) = max over N and channel

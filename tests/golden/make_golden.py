@@ -149,8 +149,24 @@ def raster_golden(name, G, W, H, seed, d0, mode, scale_mult=1.0, C=1):
     print("wrote raster_%s.npz" % name, "n_isects", meta["isect_ids"].shape[0], "edge px", int(meta["edge"].sum()))
 
 
+def camera_golden():
+    """Reference's own spline_utils.se3_to_SE3 (pure torch) on seeded 6-vectors, with autograd grads."""
+    _import_reference()
+    from flow3d.models.utils.spline_utils import se3_to_SE3
+    g = torch.Generator().manual_seed(77)
+    wu = torch.cat([0.3 * torch.randn(64, 6, generator=g), 1e-4 * torch.randn(16, 6, generator=g), torch.zeros(1, 6)])
+    wu.requires_grad_(True)
+    Rt = se3_to_SE3(wu)
+    v = torch.randn(Rt.shape, generator=g)
+    (gw,) = torch.autograd.grad((Rt * v).sum(), wu)
+    np.savez_compressed(os.path.join(HERE, "camera_se3.npz"), wu=wu.detach().numpy(), Rt=Rt.detach().numpy(),
+                        v=v.numpy(), grad_wu=gw.numpy())
+    print("wrote camera_se3.npz", tuple(Rt.shape))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    camera_golden()
     deform_golden("k6_n5", G=600, K=6, N=5, seed=11)
     deform_golden("k10_n9", G=900, K=10, N=9, seed=12)
     deform_golden("k3_n1_int", G=257, K=3, N=1, seed=13, int_ts=True)

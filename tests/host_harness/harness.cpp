@@ -9,6 +9,7 @@
 
 #include "../../deblur4dgs_b200/csrc/project_math.cuh"
 #include "../../deblur4dgs_b200/csrc/deform_math.cuh"
+#include "../../deblur4dgs_b200/csrc/camera_math.cuh"
 
 using namespace d4;
 
@@ -81,5 +82,28 @@ void hh_deform_point_vjp(const float *bl, const float *mu, const float *q, const
             grad[16 * i + a] = acc;
         }
     }
+}
+
+// camera interpolation (row a7): forward and dual-number VJP for sub-exposure parameter u
+void hh_camera_interp(const float *start6, const float *end6, const float *us, int n, float *Rt) {
+    for (int i = 0; i < n; ++i) camera_interp_one<float>(start6, end6, us[i], Rt + 12 * i);
+}
+void hh_camera_interp_vjp(const float *start6, const float *end6, const float *us, int n, const float *v,
+                          float *g12) {
+    typedef Dual<12> DU;
+    for (int j = 0; j < 12; ++j) g12[j] = 0.f;
+    for (int i = 0; i < n; ++i) {
+        DU s[6], e[6], Rt[12];
+        for (int a = 0; a < 6; ++a) {
+            s[a].v = start6[a]; e[a].v = end6[a];
+            for (int j = 0; j < 12; ++j) { s[a].d[j] = (j == a) ? 1.f : 0.f; e[a].d[j] = (j == 6 + a) ? 1.f : 0.f; }
+        }
+        camera_interp_one<DU>(s, e, us[i], Rt);
+        for (int o = 0; o < 12; ++o)
+            for (int j = 0; j < 12; ++j) g12[j] += v[12 * i + o] * Rt[o].d[j];
+    }
+}
+void hh_se3_to_SE3(const float *wu, int n, float *Rt) {
+    for (int i = 0; i < n; ++i) se3_to_SE3_mat<float>(wu + 6 * i, wu + 6 * i + 3, Rt + 12 * i);
 }
 }

@@ -405,3 +405,28 @@ def test_full_size_c3_properties():
     mass = (o2["exposure_imgs"][..., :16].double().abs() * wgt.double().abs()).sum()
     assert abs(float(lin) - float(direct)) <= 1e-6 * float(mass)
     report(test="c3_properties", kind="props", n_isects=int(ids.numel()), lin=float(lin), direct=float(direct))
+
+
+def test_camera_interpolation_a7():
+    """Row a7: N interpolated camera deltas + gradients to the two head vectors vs the oracle restatement."""
+    from deblur4dgs_b200.camera import interpolate_camera_deltas, subexposure_times
+    from oracle import camera as ocam
+    gen = torch.Generator().manual_seed(8)
+    for scale, N in [(0.2, 11), (0.01, 11), (0.01, 3), (0.0, 11), (1e-5, 9)]:
+        s6 = scale * torch.randn(1, 6, generator=gen)
+        e6 = scale * torch.randn(1, 6, generator=gen)
+        sc, ec = s6.clone().requires_grad_(True), e6.clone().requires_grad_(True)
+        ref = ocam.camera_interp(sc[0], ec[0], N)
+        sg, eg = s6.to(DEV).requires_grad_(True), e6.to(DEV).requires_grad_(True)
+        out = interpolate_camera_deltas(sg, eg, N)
+        assert out.shape == (N, 3, 4)
+        e_fwd = rel_err(out.detach().cpu().numpy(), ref.detach().numpy())
+        v = torch.randn(N, 3, 4, generator=gen)
+        (out * v.to(DEV)).sum().backward()
+        gs, ge = torch.autograd.grad((ref * v).sum(), [sc, ec])
+        e_gs, e_ge = scale_err(sg.grad.cpu().numpy(), gs.numpy()), scale_err(eg.grad.cpu().numpy(), ge.numpy())
+        report(test=f"camera_scale{scale}_N{N}", kind="camera", rel_err_fwd=e_fwd, grad_start=e_gs, grad_end=e_ge)
+        assert e_fwd <= 1e-4 and e_gs <= 2e-3 and e_ge <= 2e-3, (scale, N, e_fwd, e_gs, e_ge)
+    d = torch.tensor([0.3], device=DEV)
+    t = subexposure_times(3.0, -d, d, 5)
+    assert torch.allclose(t.cpu(), torch.tensor([2.7, 2.85, 3.0, 3.15, 3.3]), atol=1e-6)

@@ -106,3 +106,40 @@ def test_deform_point_and_dual_vjp(hh):
     err = np.abs(grad - ref) / (np.abs(ref) + 1e-3 * np.abs(ref).max(axis=1, keepdims=True) + 1e-6)
     assert np.quantile(err, 0.999) < 1e-3, np.quantile(err, [0.5, 0.99, 0.999, 1.0])
     assert scale_err(grad, ref) < 1e-4
+
+
+def test_camera_se3_pinned_to_reference_and_interp(hh):
+    """Row a7.  (1) oracle/camera.se3_to_SE3 and the product's se3_to_SE3_mat vs the fixture produced by
+    the reference's own spline_utils.se3_to_SE3; (2) the product's camera_interp_one (float and
+    Dual<12>) vs the oracle restatement and its autograd."""
+    from oracle import camera as ocam
+    from util import golden
+    g = golden("camera_se3.npz")
+    wu = torch.from_numpy(g["wu"]).requires_grad_(True)
+    Rt = ocam.se3_to_SE3(wu)
+    assert rel_err(Rt.detach().numpy(), g["Rt"]) < 1e-5
+    (gw,) = torch.autograd.grad((Rt * torch.from_numpy(g["v"])).sum(), wu)
+    assert scale_err(gw.numpy(), g["grad_wu"]) < 1e-5
+    out = np.zeros((g["wu"].shape[0], 12), np.float32)
+    wun = np.ascontiguousarray(g["wu"])
+    hh.hh_se3_to_SE3(_p(wun), wun.shape[0], _p(out))
+    assert rel_err(out.reshape(-1, 3, 4), g["Rt"]) < 1e-5
+    # interpolation: generic, tiny-angle (Taylor branches) and exactly-zero heads (the init state)
+    gen = torch.Generator().manual_seed(3)
+    for scale in (0.3, 0.01, 1e-5, 0.0):
+        s6 = (scale * torch.randn(6, generator=gen)).requires_grad_(True)
+        e6 = (scale * torch.randn(6, generator=gen)).requires_grad_(True)
+        N = 11
+        ref = ocam.camera_interp(s6, e6, N)
+        us = torch.linspace(0, 1, N).numpy().copy()
+        got = np.zeros((N, 12), np.float32)
+        sn, en = s6.detach().numpy().copy(), e6.detach().numpy().copy()
+        hh.hh_camera_interp(_p(sn), _p(en), _p(us), N, _p(got))
+        assert rel_err(got.reshape(N, 3, 4), ref.detach().numpy()) < 1e-4, scale
+        v = torch.randn(N, 3, 4, generator=gen)
+        gs, ge = torch.autograd.grad((ref * v).sum(), [s6, e6])
+        g12 = np.zeros(12, np.float32)
+        vn = v.numpy().reshape(N, 12).copy()
+        hh.hh_camera_interp_vjp(_p(sn), _p(en), _p(us), N, _p(vn), _p(g12))
+        refg = np.concatenate([gs.numpy(), ge.numpy()])
+        assert scale_err(g12, refg) < 2e-3, (scale, g12, refg)
