@@ -72,7 +72,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //             block: the ellipse {sigma <= ln(255 o)} has the bounding box
 //             |dx| <= sqrt(2 tau cov_xx), |dy| <= sqrt(2 tau cov_yy); the test is conservative
 //             (slack for rounding), so skipping never changes a result.
-template <int D>
+template <int D, bool kStageColors = true>
 __device__ __forceinline__ void stage_gaussian(const BlendArgs &a, int c, int64_t idx, bool in_range, int tr,
                                                int tile_x0, int tile_y0, float4 *s_geom, float4 *s_conic,
                                                float *s_col, uint32_t *s_mask) {
@@ -109,6 +109,7 @@ __device__ __forceinline__ void stage_gaussian(const BlendArgs &a, int c, int64_
         }
     }
     s_mask[tr] = mask;
+    if constexpr (!kStageColors) return;
     const float *col = a.colors + c * a.colors_cs + (int64_t)gl * a.D0;
     float *dst = s_col + tr * DS;
     const int d0 = a.depths ? D - 1 : D;
@@ -270,8 +271,62 @@ struct RedWidth {
     static constexpr int value = V <= 8 ? 8 : (V <= 16 ? 16 : 32);
 };
 
+// ---- tensor-core path for the colour gradients ----------------------------------------------
+// v_colors[g][ch] = sum_pixels fac[g][p] * v_out[p][ch] is a genuine dense contraction per warp:
+// [16 Gaussians x 32 pixels] x [32 pixels x 8*NT channels].  It runs on the tensor cores as
+// m16n8k8 TF32 MMAs with BOTH operands split into hi + lo TF32 parts (3 MMAs per product:
+// hi*hi + lo*hi + hi*lo, fp32 accumulate), which keeps ~2^-21 relative accuracy -- plain TF32
+// (2^-11) would break the 1e-4 parity.  tcgen05 is not applicable: its operands are CTA-wide
+// shared-memory tiles issued by one thread, these are per-warp 16x32 fragments.
+__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kFacRows = 16;    // Gaussians buffered per warp before one MMA flush
+constexpr int kFacStride = 36;  // 32 pixels + 4 pad: conflict-free A-fragment loads
+
+// Backward shared-memory budget at D = 17, 128 Gaussians per batch: geometry 4 KB + colours 10 KB +
+// accumulators 11.75 KB + slot ids 1 KB + MMA buffers (v_out 16 KB swizzled, fac 18 KB) = 61 KB
+// -> 3 CTAs (24 warps) per SM.  Measured alternatives (profiles/): 256-Gaussian batches fit only
+// 2 CTAs/SM and are latency-bound (issue slots 54 % busy); reading the colours from global memory
+// instead of staging them frees 20 KB but puts an L1 round trip on the T/S recurrence (slower).
+//
+// MEASURED at c3 (D = 17, 9 x 1.49 M intersections): the tensor-core path executes 41 % fewer
+// instructions than the all-shuffle reduction (6.2e9 vs 7.9e9 warp instructions) but is NOT faster:
+// 9.2-10.4 ms vs 8.8 ms.  Its shared-memory footprint caps occupancy, the per-warp flush adds
+// LDS / split / CAS-atomic latency, and the kernel is then bound by barrier imbalance and
+// short-scoreboard stalls rather than by issue slots.  It is therefore compiled out by default
+// (kUseMmaBwd = false) and kept for the next round (needs operands kept in registers).
+constexpr bool kUseMmaBwd = false;
+constexpr int kBatchB = kUseMmaBwd ? 128 : 256;
+
 template <int D>
-__global__ void __launch_bounds__(kBlendThreads)
+struct BwdCfg {
+    static constexpr int NT = kUseMmaBwd ? D / 8 : 0;  // n-tiles of 8 channels handled by the MMA path
+    static constexpr int DM = NT * 8;                // channels [0, DM) -> tensor cores
+    static constexpr int VSH = D - DM + 6;           // values still reduced with shuffles
+    static constexpr int RW = RedWidth<VSH>::value;
+    // s_vout row stride: DM == 16 uses an XOR swizzle (stride 16, conflict-free); otherwise a padded
+    // stride == 8 or 24 (mod 32) so that the 4 x 8 B-fragment addresses of a warp hit 32 banks
+    static constexpr bool SWZ = (DM == 16);
+    static constexpr int VOS = NT > 0 ? (SWZ ? 16 : ((DM % 16 == 8) ? DM + 16 : DM + 8)) : 0;
+    static constexpr size_t smem_bytes() {
+        return sizeof(float4) * 2 * kBatchB + sizeof(float) * kBatchB * (BlendCfg<D>::DS + (BlendCfg<D>::V | 1)) +
+               (NT > 0 ? sizeof(float) * (kBlendThreads / 32) * (32 * VOS + kFacRows * kFacStride) : 0);
+    }
+    static __device__ __forceinline__ int vout_idx(int px, int ch) {
+        return SWZ ? px * 16 + (ch ^ (((px >> 1) & 1) << 3)) : px * VOS + ch;
+    }
+};
+
+template <int D>
+__global__ void __launch_bounds__(kBlendThreads, 3)
 blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
                  const float *__restrict__ acc_depth, const float *__restrict__ v_render_colors,
                  const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
@@ -280,13 +335,19 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
     constexpr int DS = BlendCfg<D>::DS;
     constexpr int V = BlendCfg<D>::V;
     constexpr int VS = V | 1;  // odd accumulator stride
+    constexpr int NT = BwdCfg<D>::NT, DM = BwdCfg<D>::DM, VSH = BwdCfg<D>::VSH, RW = BwdCfg<D>::RW;
+    constexpr int VOS = BwdCfg<D>::VOS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_geom = reinterpret_cast<float4 *>(smem_raw);
-    float4 *s_conic = s_geom + kBatch;
-    float *s_col = reinterpret_cast<float *>(s_conic + kBatch);
-    float *s_acc = s_col + kBatch * DS;
+    float4 *s_conic = s_geom + kBatchB;
+    float *s_col = reinterpret_cast<float *>(s_conic + kBatchB);
+    float *s_acc = s_col + kBatchB * DS;
+    float *s_vout_all = s_acc + kBatchB * VS;                               // [8 warps][32 px][VOS]
+    float *s_fac_all = s_vout_all + (kBlendThreads / 32) * 32 * VOS;       // [8 warps][16][36]
     __shared__ int32_t s_max[kBlendThreads / 32];
-    __shared__ uint32_t s_mask[kBatch];
+    __shared__ uint32_t s_mask[kBatchB];
+    __shared__ int32_t s_slot[kBlendThreads / 32][kFacRows];
+    __shared__ int32_t s_gid[2][kBatchB];  // flatten ids of the batch being processed / being flushed
 
     const int n_tiles = a.tile_w * a.tile_h;
     const int ct = blockIdx.x;
@@ -341,26 +402,108 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
     // nothing behind the last contributing Gaussian of any pixel of the CTA matters
     const int32_t warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
     if (lane == 0) s_max[w] = warp_bin_final;
+    float *s_vout = s_vout_all + w * 32 * VOS;
+    float *s_fac = s_fac_all + w * kFacRows * kFacStride;
+    if constexpr (NT > 0) {
+        // B operand of the MMA path: this warp's 32 x DM block of v_out (zero-padded to VOS columns)
+#pragma unroll
+        for (int k = 0; k < DM; ++k) s_vout[BwdCfg<D>::vout_idx(lane, k)] = v_out[k];
+    }
     __syncthreads();
     int32_t block_bin_final = s_max[0];
 #pragma unroll
     for (int k = 1; k < kBlendThreads / 32; ++k) block_bin_final = max(block_bin_final, s_max[k]);
     range_end = min(range_end, (int64_t)block_bin_final + 1);
     if (range_end <= range_start) return;
-    const int num_batches = (int)((range_end - range_start + kBatch - 1) / kBatch);
+    const int num_batches = (int)((range_end - range_start + kBatchB - 1) / kBatchB);
 
-    constexpr int RW = RedWidth<V>::value;
-    constexpr int NCHUNK = (V + 31) / 32;
-    constexpr int RN = NCHUNK == 1 ? RW : NCHUNK * 32;
+    const int gid = lane >> 2, tig = lane & 3;
+    int nb = 0;  // Gaussians buffered in s_fac (warp-uniform)
+
+    // one MMA flush: s_acc[slot[row]][ch] += sum_p s_fac[row][p] * s_vout[p][ch], rows < nb
+    auto flush_colors = [&]() {
+        if constexpr (NT > 0) {
+            __syncwarp();
+            float acc[NT][4];
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[n][q] = 0.f;
+            const bool r0ok = gid < nb, r1ok = gid + 8 < nb;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int c0 = ks * 8 + tig;
+                float af[4];
+                af[0] = r0ok ? s_fac[gid * kFacStride + c0] : 0.f;
+                af[1] = r1ok ? s_fac[(gid + 8) * kFacStride + c0] : 0.f;
+                af[2] = r0ok ? s_fac[gid * kFacStride + c0 + 4] : 0.f;
+                af[3] = r1ok ? s_fac[(gid + 8) * kFacStride + c0 + 4] : 0.f;
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tf32_split(af[q], ah[q], al[q]);
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    uint32_t bh0, bl0, bh1, bl1;
+                    tf32_split(s_vout[BwdCfg<D>::vout_idx(c0, n * 8 + gid)], bh0, bl0);
+                    tf32_split(s_vout[BwdCfg<D>::vout_idx(c0 + 4, n * 8 + gid)], bh1, bl1);
+                    mma_tf32(acc[n], ah, bh0, bh1);
+                    mma_tf32(acc[n], al, bh0, bh1);
+                    mma_tf32(acc[n], ah, bl0, bl1);
+                }
+            }
+            const int slot0 = r0ok ? s_slot[w][gid] : 0, slot1 = r1ok ? s_slot[w][gid + 8] : 0;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const int ch = n * 8 + tig * 2;
+                if (r0ok) {
+                    if (acc[n][0] != 0.f) atomicAdd(&s_acc[slot0 * VS + ch], acc[n][0]);
+                    if (acc[n][1] != 0.f) atomicAdd(&s_acc[slot0 * VS + ch + 1], acc[n][1]);
+                }
+                if (r1ok) {
+                    if (acc[n][2] != 0.f) atomicAdd(&s_acc[slot1 * VS + ch], acc[n][2]);
+                    if (acc[n][3] != 0.f) atomicAdd(&s_acc[slot1 * VS + ch + 1], acc[n][3]);
+                }
+            }
+            __syncwarp();
+            nb = 0;
+        }
+    };
+
+    // flush of one batch's CTA-level sums: one global atomic per non-zero (Gaussian, value); zeroes as it goes
+    auto flush_acc = [&](int n_slots, const int32_t *gids) {
+        const int d0 = a.depths ? D - 1 : D;
+        for (int e = tid; e < n_slots * V; e += kBlendThreads) {
+            const int t = e / V, k = e - t * V;
+            const float val = s_acc[t * VS + k];
+            if (val == 0.f) continue;
+            s_acc[t * VS + k] = 0.f;
+            const int32_t g = gids[t];
+            const int32_t gl = g - c * a.G;
+            float *dst;
+            if (k < d0) dst = v_colors + c * a.colors_cs + (int64_t)gl * a.D0 + k;
+            else if (k < D) dst = v_depths + g;
+            else if (k < D + 3) dst = v_conics + 3LL * g + (k - D);
+            else if (k < D + 5) dst = v_means2d + 2LL * g + (k - D - 3);
+            else dst = v_opacities + gl;
+            atomicAdd(dst, val);
+        }
+    };
+    for (int e = tid; e < kBatchB * VS; e += kBlendThreads) s_acc[e] = 0.f;
+    int prev_size = 0;
 
     for (int b = 0; b < num_batches; ++b) {
-        __syncthreads();  // previous batch fully consumed (s_* reuse) and flushed
-        const int64_t batch_end = range_end - 1 - (int64_t)kBatch * b;  // slot 0 = furthest back
-        const int batch_size = (int)min((int64_t)kBatch, batch_end + 1 - range_start);
-        stage_gaussian<D>(a, c, batch_end - tid, batch_end - tid >= range_start, tid, tx * kTile, ty * kTile, s_geom,
-                          s_conic, s_col, s_mask);
-        for (int e = tid; e < kBatch * VS; e += kBlendThreads) s_acc[e] = 0.f;
-        __syncthreads();
+        // (barrier C of the previous iteration has passed: every warp is done with batch b-1)
+        const int64_t batch_end = range_end - 1 - (int64_t)kBatchB * b;  // slot 0 = furthest back
+        const int batch_size = (int)min((int64_t)kBatchB, batch_end + 1 - range_start);
+        if (tid < kBatchB) {
+            const bool in_range = batch_end - tid >= range_start;
+            stage_gaussian<D>(a, c, batch_end - tid, in_range, tid, tx * kTile, ty * kTile, s_geom, s_conic, s_col,
+                              s_mask);
+            s_gid[b & 1][tid] = in_range ? __ldg(a.flatten_ids + (batch_end - tid)) : 0;
+        }
+        flush_acc(prev_size, s_gid[(b & 1) ^ 1]);  // overlaps the staging loads of this batch
+        prev_size = batch_size;
+        __syncthreads();  // barrier B: staging visible, accumulators clean
 
         const int t0 = (int)max((int64_t)0, batch_end - (int64_t)warp_bin_final);
         for (int chunk = t0 >> 5; chunk * 32 < batch_size; ++chunk) {
@@ -378,27 +521,31 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
                 const bool valid = (batch_end - t <= (int64_t)bin_final) && power <= g0.z && alpha >= kAlphaMin;
                 if (!__any_sync(0xffffffffu, valid)) continue;
 
-                float r[RN];
+                constexpr int RSZ = VSH <= 8 ? 8 : (VSH <= 16 ? 16 : (VSH <= 24 ? 24 : (VSH <= 32 ? 32 : 40)));
+                float r[RSZ];
 #pragma unroll
-                for (int k = 0; k < RN; ++k) r[k] = 0.f;
+                for (int k = 0; k < RSZ; ++k) r[k] = 0.f;
+                float fac = 0.f;
                 if (valid) {
                     const float ra = __fdividef(1.0f, 1.0f - alpha);  // alpha <= 0.999: MUFU.RCP is within 1 ulp here
                     T *= ra;
-                    const float fac = alpha * T;
+                    fac = alpha * T;
+                    // s = <c_g, v_out>, four independent partial sums (short dependency chain)
                     const float *cp = s_col + t * DS;
-                    float s = 0.f;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                     for (int k4 = 0; k4 < D / 4; ++k4) {
                         const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
-                        s = fmaf(cv.x, v_out[4 * k4 + 0], s);
-                        s = fmaf(cv.y, v_out[4 * k4 + 1], s);
-                        s = fmaf(cv.z, v_out[4 * k4 + 2], s);
-                        s = fmaf(cv.w, v_out[4 * k4 + 3], s);
+                        s0 = fmaf(cv.x, v_out[4 * k4 + 0], s0);
+                        s1 = fmaf(cv.y, v_out[4 * k4 + 1], s1);
+                        s2 = fmaf(cv.z, v_out[4 * k4 + 2], s2);
+                        s3 = fmaf(cv.w, v_out[4 * k4 + 3], s3);
                     }
 #pragma unroll
-                    for (int k = D / 4 * 4; k < D; ++k) s = fmaf(cp[k], v_out[k], s);
+                    for (int k = D / 4 * 4; k < D; ++k) s0 = fmaf(cp[k], v_out[k], s0);
+                    const float s = (s0 + s1) + (s2 + s3);
 #pragma unroll
-                    for (int k = 0; k < D; ++k) r[k] = fac * v_out[k];
+                    for (int k = DM; k < D; ++k) r[k - DM] = fac * v_out[k];  // channels not on the MMA path
                     const float v_alpha = s * T - (S - tail) * ra;
                     S = fmaf(s, fac, S);
                     if (araw <= kAlphaMax) {
@@ -406,17 +553,24 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
                         //   a dx + b dy = -(2 A' dx + B' dy) / log2e
                         const float v_sigma = -araw * v_alpha;
                         const float vs2 = v_sigma * (-1.0f / kLog2e);
-                        r[D + 0] = 0.5f * v_sigma * dx * dx;
-                        r[D + 1] = v_sigma * dx * dy;
-                        r[D + 2] = 0.5f * v_sigma * dy * dy;
-                        r[D + 3] = vs2 * fmaf(2.0f * cn.x, dx, cn.y * dy);
-                        r[D + 4] = vs2 * fmaf(cn.y, dx, 2.0f * cn.z * dy);
-                        r[D + 5] = araw * cn.w * v_alpha;  // exp(-sigma) * v_alpha
+                        r[D - DM + 0] = 0.5f * v_sigma * dx * dx;
+                        r[D - DM + 1] = v_sigma * dx * dy;
+                        r[D - DM + 2] = 0.5f * v_sigma * dy * dy;
+                        r[D - DM + 3] = vs2 * fmaf(2.0f * cn.x, dx, cn.y * dy);
+                        r[D - DM + 4] = vs2 * fmaf(cn.y, dx, 2.0f * cn.z * dy);
+                        r[D - DM + 5] = araw * cn.w * v_alpha;  // exp(-sigma) * v_alpha
                     }
                 }
-                // warp reduction of the V partial sums, then CTA-level accumulation
-                if constexpr (V > 16 && V <= 24) {
-                    // 16 + 8 split: 16 + 9 shuffles instead of 31 for the padded 32-wide butterfly
+                if constexpr (NT > 0) {
+                    // buffer this Gaussian's per-pixel weights for the tensor-core flush
+                    s_fac[nb * kFacStride + lane] = fac;
+                    if (lane == 0) s_slot[w][nb] = t;
+                    ++nb;
+                }
+                // shuffle path: the remaining VSH values; lane j < VSH ends up owning value j
+                float mine;
+                if constexpr (VSH > 16 && VSH <= 24) {
+                    // 16 + 8 split: 16 + 9 shuffles instead of 31 for a padded 32-wide butterfly
                     float ra16[16], rb8[8];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) ra16[k] = r[k];
@@ -424,44 +578,39 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
                     for (int k = 0; k < 8; ++k) rb8[k] = r[16 + k];
                     warp_transpose_reduce<16>(ra16, lane);
                     warp_transpose_reduce<8>(rb8, lane);
-                    // lanes 0-15 own values 0-15, lanes 16-23 own values 16-23
-                    const float mine = lane < 16 ? ra16[0] : rb8[0];
-                    if (lane < V) atomicAdd(&s_acc[t * VS + lane], mine);
-                } else if constexpr (NCHUNK == 1) {
-                    warp_transpose_reduce<RN>(r, lane);
-                    const int slot = lane & (RW - 1);
-                    if (lane < RW && slot < V) atomicAdd(&s_acc[t * VS + slot], r[0]);
-                } else {
+                    mine = lane < 16 ? ra16[0] : rb8[0];
+                } else if constexpr (VSH > 32) {
+                    static_assert(VSH <= 40, "too many shuffle-reduced values");
+                    float ra32[32], rb8[8];
 #pragma unroll
-                    for (int ch = 0; ch < NCHUNK; ++ch) {
-                        float rr[32];
+                    for (int k = 0; k < 32; ++k) ra32[k] = r[k];
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) rr[k] = r[ch * 32 + k];
-                        warp_transpose_reduce<32>(rr, lane);
-                        const int slot = ch * 32 + lane;
-                        if (slot < V) atomicAdd(&s_acc[t * VS + slot], rr[0]);
+                    for (int k = 0; k < 8; ++k) rb8[k] = r[32 + k];
+                    warp_transpose_reduce<32>(ra32, lane);
+                    warp_transpose_reduce<8>(rb8, lane);
+                    mine = ra32[0];
+                    if (lane < VSH - 32) {  // values 32.. are owned a second time by lanes 0..VSH-33
+                        const int j = 32 + lane;
+                        const int idx2 = j < D - DM ? DM + j : D + (j - (D - DM));
+                        atomicAdd(&s_acc[t * VS + idx2], rb8[0]);
                     }
+                } else {
+                    warp_transpose_reduce<RW>(r, lane);
+                    mine = r[0];
+                }
+                if (lane < (VSH < 32 ? VSH : 32)) {
+                    const int idx = lane < D - DM ? DM + lane : D + (lane - (D - DM));
+                    atomicAdd(&s_acc[t * VS + idx], mine);
+                }
+                if constexpr (NT > 0) {
+                    if (nb == kFacRows) flush_colors();
                 }
             }
         }
-        __syncthreads();
-        // flush: one global atomic per non-zero (Gaussian, value) of this tile
-        const int d0 = a.depths ? D - 1 : D;
-        for (int e = tid; e < batch_size * V; e += kBlendThreads) {
-            const int t = e / V, k = e - t * V;
-            const float val = s_acc[t * VS + k];
-            if (val == 0.f) continue;
-            const int32_t g = __float_as_int(s_geom[t].w);
-            const int32_t gl = g - c * a.G;
-            float *dst;
-            if (k < d0) dst = v_colors + c * a.colors_cs + (int64_t)gl * a.D0 + k;
-            else if (k < D) dst = v_depths + g;
-            else if (k < D + 3) dst = v_conics + 3LL * g + (k - D);
-            else if (k < D + 5) dst = v_means2d + 2LL * g + (k - D - 3);
-            else dst = v_opacities + gl;
-            atomicAdd(dst, val);
-        }
+        if (nb > 0) flush_colors();
+        __syncthreads();  // barrier C: every warp is done with batch b
     }
+    flush_acc(prev_size, s_gid[(num_batches & 1) ^ 1]);
 }
 
 // ----------------------------------------------------------------------------- dispatch
@@ -475,7 +624,7 @@ template <int D>
 static int launch_bwd(const BlendArgs &a, const float *ra, const int32_t *li, const float *ad, const float *vrc,
                       const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd, cudaStream_t st) {
     int grid = a.C * a.tile_w * a.tile_h;
-    constexpr size_t smem = sizeof(float4) * 2 * kBatch + sizeof(float) * kBatch * (BlendCfg<D>::DS + (BlendCfg<D>::V | 1));
+    constexpr size_t smem = BwdCfg<D>::smem_bytes();
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(blend_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
