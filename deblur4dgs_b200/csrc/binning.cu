@@ -247,9 +247,153 @@ tile_offsets_kernel(const int64_t *__restrict__ ids, int64_t n, int n_tiles, int
     for (int64_t t = cur + 1; t <= nxt && t < total; ++t) offsets[t] = (int32_t)(idx + 1);
 }
 
+// ----------------------------------------------------------------------------- tile-bucketed binning
+// B200-first alternative to "emit + 6-pass global radix sort" (gsplat's structure): the sort key is
+// (camera, tile | depth), and every (camera, tile) segment is small (hundreds to a few thousand
+// entries), so
+//   (1) count intersections per (camera, tile)      -> exclusive scan == isect_offsets directly,
+//   (2) emit every intersection straight into its tile's segment (unordered, atomic cursor),
+//   (3) one CTA per tile sorts its segment in SHARED MEMORY by the unique 64-bit key
+//       (depth bits << 32 | flatten id) with a bitonic network and writes the final lists.
+// ~20-28 B of HBM traffic per intersection instead of 6 passes x 36 B.  The result is bit-identical
+// to the stable radix sort: ties in depth are ordered by flatten id, which is emission order.
+constexpr int kTileSortMax = 4096;  // segment capacity of the shared-memory sort (32 KB of keys)
+
+__device__ __forceinline__ void tile_rect_dev(float m2x, float m2y, int32_t radius, int tile_size, int tile_w,
+                                              int tile_h, int &x0, int &y0, int &x1, int &y1) {
+    // identical arithmetic to project_math.cuh::tile_rect (exact: divisions by the tile size, floor / ceil)
+    const float ts = (float)tile_size;
+    const float tr = __fdiv_rn((float)radius, ts);
+    const float tx = __fdiv_rn(m2x, ts), ty = __fdiv_rn(m2y, ts);
+    const float fw = (float)tile_w, fh = (float)tile_h;
+    x0 = (int)fminf(fmaxf(floorf(__fsub_rn(tx, tr)), 0.f), fw);
+    y0 = (int)fminf(fmaxf(floorf(__fsub_rn(ty, tr)), 0.f), fh);
+    x1 = (int)fminf(fmaxf(ceilf(__fadd_rn(tx, tr)), 0.f), fw);
+    y1 = (int)fminf(fmaxf(ceilf(__fadd_rn(ty, tr)), 0.f), fh);
+}
+
+__global__ void __launch_bounds__(256)
+tile_count_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii, int C, int G, int tile_size,
+                  int tile_w, int tile_h, int32_t *__restrict__ tile_counts) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)C * G) return;
+    const int32_t r = radii[idx];
+    if (r <= 0) return;
+    const float2 m2 = __ldg(reinterpret_cast<const float2 *>(means2d) + idx);
+    int x0, y0, x1, y1;
+    tile_rect_dev(m2.x, m2.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+    int32_t *cnt = tile_counts + (idx / G) * (int64_t)tile_w * tile_h;
+    for (int i = y0; i < y1; ++i)
+        for (int j = x0; j < x1; ++j) atomicAdd(cnt + i * tile_w + j, 1);
+}
+
+__global__ void __launch_bounds__(256)
+bucket_emit_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
+                   const float *__restrict__ depths, int C, int G, int tile_size, int tile_w, int tile_h,
+                   const int32_t *__restrict__ tile_offsets, int32_t *__restrict__ cursors,
+                   uint64_t *__restrict__ bucket_keys) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)C * G) return;
+    const int32_t r = radii[idx];
+    if (r <= 0) return;
+    const float2 m2 = __ldg(reinterpret_cast<const float2 *>(means2d) + idx);
+    int x0, y0, x1, y1;
+    tile_rect_dev(m2.x, m2.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+    const int64_t cbase = (idx / G) * (int64_t)tile_w * tile_h;
+    const uint64_t key = ((uint64_t)(uint32_t)__float_as_int(depths[idx]) << 32) | (uint32_t)idx;
+    for (int i = y0; i < y1; ++i)
+        for (int j = x0; j < x1; ++j) {
+            const int64_t t = cbase + i * tile_w + j;
+            const int32_t pos = tile_offsets[t] + atomicAdd(cursors + t, 1);
+            bucket_keys[pos] = key;
+        }
+}
+
+__global__ void __launch_bounds__(256)
+tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__restrict__ tile_offsets, int64_t n_isects,
+                 int64_t n_segments, int n_tiles, int tile_n_bits, int64_t *__restrict__ isect_ids,
+                 int32_t *__restrict__ flatten_ids) {
+    extern __shared__ uint64_t s_keys[];
+    const int64_t seg = blockIdx.x;
+    const int32_t start = tile_offsets[seg];
+    const int32_t end = (seg == n_segments - 1) ? (int32_t)n_isects : tile_offsets[seg + 1];
+    const int n = end - start;
+    if (n <= 0) return;
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[i] = i < n ? bucket_keys[start + i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (n_pad >> 1); i += blockDim.x) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const uint64_t a = s_keys[lo], b = s_keys[hi];
+                const bool asc = (lo & k) == 0;
+                if ((a > b) == asc) {
+                    s_keys[lo] = b;
+                    s_keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int64_t cam = seg / n_tiles, tile = seg - cam * n_tiles;
+    const int64_t hi_bits = (cam << (32 + tile_n_bits)) | (tile << 32);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = s_keys[i];
+        flatten_ids[start + i] = (int32_t)(uint32_t)key;
+        isect_ids[start + i] = hi_bits | (int64_t)(key >> 32);
+    }
+}
+
 }  // namespace d4
 
 using namespace d4;
+
+extern "C" int d4_tile_sort_capacity(void) { return kTileSortMax; }
+
+extern "C" int d4_tile_count(const float *means2d, const int32_t *radii, int C, int G, int tile_size, int tile_w,
+                             int tile_h, int32_t *tile_counts, d4_stream_t stream) {
+    D4_CHECK_ARG(C >= 1 && G >= 0 && tile_counts, "d4_tile_count: bad arguments");
+    if (G == 0) return 0;
+    D4_CHECK_ARG(means2d && radii, "d4_tile_count: null pointer");
+    tile_count_kernel<<<cdiv((int64_t)C * G, 256), 256, 0, as_stream(stream)>>>(means2d, radii, C, G, tile_size, tile_w,
+                                                                               tile_h, tile_counts);
+    D4_CHECK_LAUNCH("d4_tile_count");
+    return 0;
+}
+
+extern "C" int d4_bucket_emit(const float *means2d, const int32_t *radii, const float *depths, int C, int G,
+                              int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets, int32_t *cursors,
+                              uint64_t *bucket_keys, d4_stream_t stream) {
+    D4_CHECK_ARG(C >= 1 && G >= 0 && (int64_t)C * G < (1LL << 32), "d4_bucket_emit: bad sizes");
+    if (G == 0) return 0;
+    D4_CHECK_ARG(means2d && radii && depths && tile_offsets && cursors && bucket_keys, "d4_bucket_emit: null pointer");
+    bucket_emit_kernel<<<cdiv((int64_t)C * G, 256), 256, 0, as_stream(stream)>>>(
+        means2d, radii, depths, C, G, tile_size, tile_w, tile_h, tile_offsets, cursors, bucket_keys);
+    D4_CHECK_LAUNCH("d4_bucket_emit");
+    return 0;
+}
+
+extern "C" int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,
+                            int tile_w, int tile_h, int max_count, int64_t *isect_ids, int32_t *flatten_ids,
+                            d4_stream_t stream) {
+    D4_CHECK_ARG(C >= 1 && tile_w >= 1 && tile_h >= 1 && n_isects >= 0, "d4_tile_sort: bad arguments");
+    D4_CHECK_ARG(max_count <= kTileSortMax, "d4_tile_sort: a tile holds %d intersections, capacity is %d "
+                                            "(use d4_isect_emit + d4_sort_pairs_u64)", max_count, kTileSortMax);
+    if (n_isects == 0) return 0;
+    D4_CHECK_ARG(bucket_keys && tile_offsets && isect_ids && flatten_ids, "d4_tile_sort: null pointer");
+    int n_pad = 1;
+    while (n_pad < max_count) n_pad <<= 1;
+    const size_t smem = sizeof(uint64_t) * (size_t)n_pad;
+    const int64_t n_seg = (int64_t)C * tile_w * tile_h;
+    tile_sort_kernel<<<(unsigned)n_seg, 256, smem, as_stream(stream)>>>(bucket_keys, tile_offsets, n_isects, n_seg,
+                                                                        tile_w * tile_h, d4_tile_n_bits(tile_w * tile_h),
+                                                                        isect_ids, flatten_ids);
+    D4_CHECK_LAUNCH("d4_tile_sort");
+    return 0;
+}
 
 extern "C" size_t d4_scan_workspace_bytes(int64_t n) {
     return sizeof(int64_t) * (size_t)(cdiv(n > 0 ? n : 1, kScanTile) + 1);

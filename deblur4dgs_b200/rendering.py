@@ -31,6 +31,7 @@ from ._cabi import call, ptr, stream_ptr
 
 SUPPORTED_D = (1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32, 33)
 CHANNEL_CHUNK = 32
+BINNING_METHOD = "auto"  # "auto" | "bucket" | "radix" (see bin_tiles)
 
 
 def _check_cuda(*ts):
@@ -183,6 +184,53 @@ def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height:
     return offsets
 
 
+@torch.no_grad()
+def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+              tiles_per_gauss: Optional[Tensor] = None, method: str = "auto"):
+    """Tile binning, both halves of SURVEY row a9 in one call: returns
+    (isect_ids i64 [I], flatten_ids i32 [I], isect_offsets i32 [C,th,tw]) -- exactly what
+    gsplat.isect_tiles + gsplat.isect_offset_encode produce.
+
+    method "bucket": count per (camera, tile) -> scan (== offsets) -> emit into tile segments ->
+    per-tile shared-memory sort; "radix": gsplat's structure (emit, global LSD radix sort, offset
+    encode); "auto": bucket unless a tile holds more entries than the shared-memory sort can take."""
+    _check_cuda(means2d, radii, depths)
+    C, G = radii.shape
+    dev = means2d.device
+    st = stream_ptr()
+    n_seg = C * tile_width * tile_height
+    if method == "radix":
+        _, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
+                                                tiles_per_gauss=tiles_per_gauss)
+        return isect_ids, flatten_ids, isect_offset_encode(isect_ids, C, tile_width, tile_height)
+    counts = torch.zeros((n_seg + 1,), dtype=torch.int32, device=dev)  # last slot: scratch for the max
+    call("d4_tile_count", ptr(means2d), ptr(radii), C, G, tile_size, tile_width, tile_height, ptr(counts), st)
+    offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
+    stats = torch.empty((2,), dtype=torch.int64, device=dev)
+    ws_bytes = _cabi.lib().d4_scan_workspace_bytes(n_seg)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    call("d4_exclusive_scan_i32", ptr(counts), n_seg, ptr(offsets), ptr(stats), ptr(ws), ws_bytes, st)
+    stats[1] = counts[:n_seg].max() if n_seg > 0 else 0
+    n_isects, max_count = (int(x) for x in stats.tolist())  # the one device->host sync of the op
+    if n_isects >= 2 ** 31:
+        raise _cabi.D4Error("more than 2^31 tile intersections")
+    if max_count > _cabi.lib().d4_tile_sort_capacity():
+        if method == "bucket":
+            raise _cabi.D4Error(f"a tile holds {max_count} intersections: beyond the shared-memory sort capacity")
+        return bin_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss, method="radix")
+    isect_ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
+    flatten_ids = torch.empty((n_isects,), dtype=torch.int32, device=dev)
+    if n_isects == 0:
+        return isect_ids, flatten_ids, offsets
+    keys = torch.empty((n_isects,), dtype=torch.int64, device=dev)
+    cursors = torch.zeros((n_seg,), dtype=torch.int32, device=dev)
+    call("d4_bucket_emit", ptr(means2d), ptr(radii), ptr(depths), C, G, tile_size, tile_width, tile_height,
+         ptr(offsets), ptr(cursors), ptr(keys), st)
+    call("d4_tile_sort", ptr(keys), ptr(offsets), n_isects, C, tile_width, tile_height, max_count, ptr(isect_ids),
+         ptr(flatten_ids), st)
+    return isect_ids, flatten_ids, offsets
+
+
 # --------------------------------------------------------------------------- #
 # blend (SURVEY rows a10 + a11)
 # --------------------------------------------------------------------------- #
@@ -313,9 +361,8 @@ def rasterization(
         means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size)
     C = radii.shape[0]
     tile_width, tile_height = math.ceil(width / tile_size), math.ceil(height / tile_size)
-    _, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
-                                            tiles_per_gauss=tiles_per_gauss)
-    isect_offsets = isect_offset_encode(isect_ids, C, tile_width, tile_height)
+    isect_ids, flatten_ids, isect_offsets = bin_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
+                                                      tiles_per_gauss=tiles_per_gauss, method=BINNING_METHOD)
 
     meta = {
         "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d, "depths": depths,

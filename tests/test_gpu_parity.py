@@ -430,3 +430,34 @@ def test_camera_interpolation_a7():
     d = torch.tensor([0.3], device=DEV)
     t = subexposure_times(3.0, -d, d, 5)
     assert torch.allclose(t.cpu(), torch.tensor([2.7, 2.85, 3.0, 3.15, 3.3]), atol=1e-6)
+
+
+def test_bucket_binning_equals_radix_binning():
+    """The tile-bucketed binning (count / scan / segment emit / shared-memory sort) must reproduce the
+    gsplat-structured path (emit / stable radix sort / offset encode) bit for bit, and fall back when a
+    tile overflows the shared-memory sort."""
+    from deblur4dgs_b200 import _cabi
+    from deblur4dgs_b200.rendering import bin_tiles, fully_fused_projection
+    for G, W, H, C, scale_mult in [(30000, 320, 192, 3, 1.5), (2000, 64, 48, 1, 12.0), (50, 33, 17, 2, 1.0)]:
+        sc = make_scene(G=G, width=W, height=H, K=4, N=1, seed=G, scale_mult=scale_mult)
+        inp = scene_inputs(sc, 3, C)
+        # many exactly equal depths: ties must be ordered by flatten id
+        inp["means"][: G // 2, 2] = np.round(inp["means"][: G // 2, 2] * 2) / 2
+        radii, means2d, depths, conics, tpg = fully_fused_projection(T(inp["means"]), T(inp["quats"]), T(inp["scales"]),
+                                                                     T(inp["viewmats"]), T(inp["Ks"]), W, H)
+        tw, th = math.ceil(W / 16), math.ceil(H / 16)
+        a = bin_tiles(means2d, radii, depths, 16, tw, th, tpg, method="radix")
+        b = bin_tiles(means2d, radii, depths, 16, tw, th, tpg, method="auto")
+        for x, y, name in zip(a, b, ["isect_ids", "flatten_ids", "isect_offsets"]):
+            assert torch.equal(x, y), (G, name)
+    # overflow: > capacity intersections in one tile -> "bucket" refuses, "auto" falls back to radix
+    cap = _cabi.lib().d4_tile_sort_capacity()
+    G = cap + 500
+    means = torch.zeros(G, 3); means[:, 2] = torch.linspace(2, 3, G)
+    args = (T(means.numpy()), T(np.tile([1.0, 0, 0, 0], (G, 1)).astype(np.float32)), T(np.full((G, 3), 0.01, np.float32)),
+            T(np.eye(4, dtype=np.float32)[None]), T(np.array([[[20.0, 0, 8], [0, 20, 8], [0, 0, 1]]], np.float32)), 16, 16)
+    radii, means2d, depths, conics, tpg = fully_fused_projection(*args)
+    with pytest.raises(_cabi.D4Error):
+        bin_tiles(means2d, radii, depths, 16, 1, 1, tpg, method="bucket")
+    ids, fl, off = bin_tiles(means2d, radii, depths, 16, 1, 1, tpg, method="auto")
+    assert ids.numel() == G and bool((ids[1:] >= ids[:-1]).all())
