@@ -39,6 +39,8 @@ PROTOTYPES = {
     "d4_blend_bwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P, P, P, P, P, P]),
     "d4_deform_fwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P]),
     "d4_deform_bwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "d4_compute_transforms_fwd": (c_int, [P, P, P, P, I, I, I, I, P, P]),
+    "d4_compute_transforms_bwd": (c_int, [P, P, P, P, I, I, I, I, P, P, P, P, P, P]),
     "d4_camera_interp_fwd": (c_int, [P, P, I, P, P]),
     "d4_camera_interp_bwd": (c_int, [P, P, I, P, P, P, P]),
     "d4_combine_fwd": (c_int, [P, P, I, L, I, I, I, I, P, P, P]),

@@ -362,9 +362,167 @@ deform_bg_bwd_kernel(const float *__restrict__ bg_means, const float *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------- compute_transforms
+// MotionBases.compute_transforms (params.py:142-180) as a stand-alone op for its other callers
+// (trainer.py:478,485,701; init_utils.py:322): coefs are ALREADY softmaxed, out [G,B,3,4] = [R | t].
+__global__ void __launch_bounds__(kDefThreads)
+transforms_fwd_kernel(const float *__restrict__ coefs, const float *__restrict__ rots,
+                      const float *__restrict__ transls, const float *__restrict__ ts, int G, int K, int T, int B,
+                      float *__restrict__ out) {
+    extern __shared__ float s_coef_all[];
+    const int g = blockIdx.x * kDefThreads + threadIdx.x;
+    if (g >= G) return;
+    float *s_coef = s_coef_all + threadIdx.x;
+    for (int k = 0; k < K; ++k) s_coef[k * kDefThreads] = __ldg(coefs + (int64_t)g * K + k);
+    for (int b = 0; b < B; ++b) {
+        const FramePair f = frame_pair(__ldg(ts + b), T);
+        float bp[9], bn[9], bl[9];
+        blend_bases(s_coef, K, T, f.pre, rots, transls, bp);
+        blend_bases(s_coef, K, T, f.nxt, rots, transls, bn);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) bl[j] = (1.0f - f.w) * bp[j] + f.w * bn[j];
+        float x[3], y[3], z[3];
+        rot6d_to_cols<float>(bl + 3, x, y, z);
+        float4 *o = reinterpret_cast<float4 *>(out + ((int64_t)g * B + b) * 12);
+        o[0] = make_float4(x[0], y[0], z[0], bl[0]);
+        o[1] = make_float4(x[1], y[1], z[1], bl[1]);
+        o[2] = make_float4(x[2], y[2], z[2], bl[2]);
+    }
+}
+
+__global__ void __launch_bounds__(kDefThreads)
+transforms_bwd_kernel(const float *__restrict__ coefs, const float *__restrict__ rots,
+                      const float *__restrict__ transls, const float *__restrict__ ts, int G, int K, int T, int B,
+                      const float *__restrict__ v_out, float *__restrict__ v_coefs, float *__restrict__ v_rots,
+                      float *__restrict__ v_transls, float *__restrict__ v_ts) {
+    extern __shared__ float smem[];
+    float *s_coef_all = smem;                     // [K][kDefThreads]
+    float *s_vcoef_all = smem + K * kDefThreads;  // [K][kDefThreads]
+    float *s_vB = smem + 2 * K * kDefThreads;     // [K][9]
+    float *s_red = s_vB + K * 9;                  // [16], slot 15 = time gradient
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = blockIdx.x * kDefThreads + tid;
+    const bool active = g < G;
+    float *s_coef = s_coef_all + tid, *s_vcoef = s_vcoef_all + tid;
+    for (int k = 0; k < K; ++k) {
+        s_coef[k * kDefThreads] = active ? __ldg(coefs + (int64_t)g * K + k) : 0.f;
+        s_vcoef[k * kDefThreads] = 0.f;
+    }
+    for (int b = 0; b < B; ++b) {
+        for (int e = tid; e < K * 9 + 16; e += kDefThreads) s_vB[e] = 0.f;
+        __syncthreads();
+        const FramePair f = frame_pair(__ldg(ts + b), T);
+        float vb[9], r16[16];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) vb[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r16[j] = 0.f;
+        if (active) {
+            float bp[9], bn[9], bl[9];
+            blend_bases(s_coef, K, T, f.pre, rots, transls, bp);
+            blend_bases(s_coef, K, T, f.nxt, rots, transls, bn);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) bl[j] = (1.0f - f.w) * bp[j] + f.w * bn[j];
+            const float4 *vo = reinterpret_cast<const float4 *>(v_out + ((int64_t)g * B + b) * 12);
+            const float4 v0 = __ldg(vo), v1 = __ldg(vo + 1), v2 = __ldg(vo + 2);
+            const float vx[3] = {v0.x, v1.x, v2.x}, vy[3] = {v0.y, v1.y, v2.y}, vz[3] = {v0.z, v1.z, v2.z};
+            vb[0] = v0.w; vb[1] = v1.w; vb[2] = v2.w;
+            typedef Dual<6> DU;
+            DU r6[6], x[3], y[3], z[3];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                r6[a].v = bl[3 + a];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) r6[a].d[c] = (a == c) ? 1.f : 0.f;
+            }
+            rot6d_to_cols<DU>(r6, x, y, z);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) acc += vx[i] * x[i].d[a] + vy[i] * y[i].d[a] + vz[i] * z[i].d[a];
+                vb[3 + a] = acc;
+            }
+            float vw = 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) vw += (bn[j] - bp[j]) * vb[j];
+            r16[15] = vw;
+            for (int k = 0; k < K; ++k) {
+                const float *tp = transls + ((int64_t)k * T + f.pre) * 3, *tn = transls + ((int64_t)k * T + f.nxt) * 3;
+                const float *rp = rots + ((int64_t)k * T + f.pre) * 6, *rn = rots + ((int64_t)k * T + f.nxt) * 6;
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc += ((1.0f - f.w) * __ldg(tp + j) + f.w * __ldg(tn + j)) * vb[j];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc += ((1.0f - f.w) * __ldg(rp + j) + f.w * __ldg(rn + j)) * vb[3 + j];
+                s_vcoef[k * kDefThreads] += acc;
+            }
+        }
+        warp_transpose_reduce_d<16>(r16, lane);
+        if (lane == 15 && r16[0] != 0.f) atomicAdd(&s_red[15], r16[0]);
+        for (int k = 0; k < K; ++k) {
+            const float ck = s_coef[k * kDefThreads];
+            float r[16];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) r[j] = ck * vb[j];
+#pragma unroll
+            for (int j = 9; j < 16; ++j) r[j] = 0.f;
+            warp_transpose_reduce_d<16>(r, lane);
+            if (lane < 9 && r[0] != 0.f) atomicAdd(&s_vB[k * 9 + lane], r[0]);
+        }
+        __syncthreads();
+        for (int e = tid; e < K * 9; e += kDefThreads) {
+            const float val = s_vB[e];
+            if (val == 0.f) continue;
+            const int k = e / 9, jj = e - 9 * k;
+            if (jj < 3) {
+                atomicAdd(v_transls + ((int64_t)k * T + f.pre) * 3 + jj, (1.0f - f.w) * val);
+                atomicAdd(v_transls + ((int64_t)k * T + f.nxt) * 3 + jj, f.w * val);
+            } else {
+                atomicAdd(v_rots + ((int64_t)k * T + f.pre) * 6 + (jj - 3), (1.0f - f.w) * val);
+                atomicAdd(v_rots + ((int64_t)k * T + f.nxt) * 6 + (jj - 3), f.w * val);
+            }
+        }
+        if (tid == 15 && s_red[15] != 0.f) atomicAdd(v_ts + b, s_red[15]);
+        __syncthreads();
+    }
+    if (active)
+        for (int k = 0; k < K; ++k) v_coefs[(int64_t)g * K + k] = s_vcoef[k * kDefThreads];
+}
+
 }  // namespace d4
 
 using namespace d4;
+
+extern "C" int d4_compute_transforms_fwd(const float *coefs, const float *rots, const float *transls, const float *ts,
+                                         int G, int K, int T, int B, float *out, d4_stream_t stream) {
+    D4_CHECK_ARG(G >= 0 && K >= 1 && K <= kMaxK && T >= 1 && B >= 1, "d4_compute_transforms_fwd: bad sizes");
+    if (G == 0) return 0;
+    D4_CHECK_ARG(coefs && rots && transls && ts && out && ((uintptr_t)out & 15) == 0,
+                 "d4_compute_transforms_fwd: null/unaligned pointer");
+    size_t smem = sizeof(float) * K * kDefThreads;
+    transforms_fwd_kernel<<<cdiv(G, kDefThreads), kDefThreads, smem, as_stream(stream)>>>(coefs, rots, transls, ts, G, K,
+                                                                                         T, B, out);
+    D4_CHECK_LAUNCH("d4_compute_transforms_fwd");
+    return 0;
+}
+
+extern "C" int d4_compute_transforms_bwd(const float *coefs, const float *rots, const float *transls, const float *ts,
+                                         int G, int K, int T, int B, const float *v_out, float *v_coefs, float *v_rots,
+                                         float *v_transls, float *v_ts, d4_stream_t stream) {
+    D4_CHECK_ARG(G >= 0 && K >= 1 && K <= kMaxK && T >= 1 && B >= 1, "d4_compute_transforms_bwd: bad sizes");
+    if (G == 0) return 0;
+    D4_CHECK_ARG(coefs && rots && transls && ts && v_out && v_coefs && v_rots && v_transls && v_ts &&
+                     ((uintptr_t)v_out & 15) == 0,
+                 "d4_compute_transforms_bwd: null/unaligned pointer");
+    size_t smem = sizeof(float) * (2 * K * kDefThreads + K * 9 + 16);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(transforms_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    transforms_bwd_kernel<<<cdiv(G, kDefThreads), kDefThreads, smem, as_stream(stream)>>>(
+        coefs, rots, transls, ts, G, K, T, B, v_out, v_coefs, v_rots, v_transls, v_ts);
+    D4_CHECK_LAUNCH("d4_compute_transforms_bwd");
+    return 0;
+}
 
 static int check_deform(const char *name, int Gf, int Gb, int K, int T, int N) {
     D4_CHECK_ARG(Gf >= 0 && Gb >= 0 && N >= 1 && T >= 1, "%s: bad sizes", name);

@@ -95,6 +95,21 @@ D4_HD Dual<ND> d_max_const(const Dual<ND> &a, float c) { return a.v >= c ? a : d
 template <typename S>
 D4_HD S d_dot3(const S *a, const S *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
+// cont_6d_to_rmat (transforms.py:41-53): Gram-Schmidt of the 6-D rotation, columns x, y, z of R
+template <typename S>
+D4_HD void rot6d_to_cols(const S *r6, S *x, S *y, S *z) {
+    const float eps = 1e-12f;
+    S an = d_max_const(d_sqrt(d_dot3(r6, r6)), eps);
+    x[0] = r6[0] / an; x[1] = r6[1] / an; x[2] = r6[2] / an;
+    S bx = r6[3] * x[0] + r6[4] * x[1] + r6[5] * x[2];
+    S yp[3] = {r6[3] - bx * x[0], r6[4] - bx * x[1], r6[5] - bx * x[2]};
+    S yn = d_max_const(d_sqrt(d_dot3(yp, yp)), eps);
+    y[0] = yp[0] / yn; y[1] = yp[1] / yn; y[2] = yp[2] / yn;
+    z[0] = x[1] * y[2] - x[2] * y[1];
+    z[1] = x[2] * y[0] - x[0] * y[2];
+    z[2] = x[0] * y[1] - x[1] * y[0];
+}
+
 // (tl, r6, mu, q_raw[wxyz]) -> (mu' = R mu + tl, q' = normalize(wxyz(quat(R) (x) xyzw(normalize(q_raw)))))
 template <typename S>
 D4_HD void deform_point(const S *tl, const S *r6, const S *mu, const S *qraw, S *om, S *oq) {
@@ -104,13 +119,8 @@ D4_HD void deform_point(const S *tl, const S *r6, const S *mu, const S *qraw, S 
     S qd = d_max_const(qn, eps);
     S qh[4] = {qraw[0] / qd, qraw[1] / qd, qraw[2] / qd, qraw[3] / qd};
     // Gram-Schmidt (cont_6d_to_rmat): columns x, y, z
-    S an = d_max_const(d_sqrt(d_dot3(r6, r6)), eps);
-    S x[3] = {r6[0] / an, r6[1] / an, r6[2] / an};
-    S bx = r6[3] * x[0] + r6[4] * x[1] + r6[5] * x[2];
-    S yp[3] = {r6[3] - bx * x[0], r6[4] - bx * x[1], r6[5] - bx * x[2]};
-    S yn = d_max_const(d_sqrt(d_dot3(yp, yp)), eps);
-    S y[3] = {yp[0] / yn, yp[1] / yn, yp[2] / yn};
-    S z[3] = {x[1] * y[2] - x[2] * y[1], x[2] * y[0] - x[0] * y[2], x[0] * y[1] - x[1] * y[0]};
+    S x[3], y[3], z[3];
+    rot6d_to_cols(r6, x, y, z);
     // R[i][0] = x[i], R[i][1] = y[i], R[i][2] = z[i]
 #pragma unroll
     for (int i = 0; i < 3; ++i) om[i] = x[i] * mu[0] + y[i] * mu[1] + z[i] * mu[2] + tl[i];

@@ -97,3 +97,36 @@ def compute_poses_all(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots
     """SceneModel.compute_poses_all (scene_model.py:108-120): fg (deformed) first, bg (static) after."""
     m, q = deform_subexposures(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, ts, None)
     return m.permute(1, 0, 2), q.permute(1, 0, 2)
+
+
+class _ComputeTransforms(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ts, coefs, rots, transls):
+        if not coefs.is_cuda:
+            raise D4Error("deform ops need CUDA tensors: there is no CPU fallback")
+        ts, coefs, rots, transls = map(_c, (ts, coefs, rots, transls))
+        G, K = coefs.shape
+        T, B = rots.shape[1], ts.shape[0]
+        out = torch.empty((G, B, 3, 4), dtype=torch.float32, device=coefs.device)
+        call("d4_compute_transforms_fwd", ptr(coefs), ptr(rots), ptr(transls), ptr(ts), G, K, T, B, ptr(out),
+             stream_ptr())
+        ctx.save_for_backward(ts, coefs, rots, transls)
+        return out
+
+    @staticmethod
+    def backward(ctx, v_out):
+        ts, coefs, rots, transls = ctx.saved_tensors
+        G, K = coefs.shape
+        T, B = rots.shape[1], ts.shape[0]
+        v_coefs = torch.empty_like(coefs)
+        v_rots, v_transls, v_ts = torch.zeros_like(rots), torch.zeros_like(transls), torch.zeros_like(ts)
+        call("d4_compute_transforms_bwd", ptr(coefs), ptr(rots), ptr(transls), ptr(ts), G, K, T, B, ptr(_c(v_out)),
+             ptr(v_coefs), ptr(v_rots), ptr(v_transls), ptr(v_ts), stream_ptr())
+        return v_ts, v_coefs, v_rots, v_transls
+
+
+def compute_transforms(ts: Tensor, coefs: Tensor, rots: Tensor, transls: Tensor) -> Tensor:
+    """MotionBases.compute_transforms (params.py:142-180): ts [B] or [1,B] (float or integer frame
+    coordinates), coefs [G,K] already softmaxed -> transforms [G,B,3,4] = [R | t]."""
+    ts_f = ts.reshape(-1).to(torch.float32)
+    return _ComputeTransforms.apply(ts_f, coefs, rots, transls)

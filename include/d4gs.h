@@ -169,6 +169,17 @@ int d4_deform_bwd(const float *fg_means, const float *fg_quats, const float *mot
                   float *v_bg_quats, float *v_rots, float *v_transls, float *v_times, float *v_RTs,
                   d4_stream_t stream);
 
+/* ---- a2/a3 stand-alone: MotionBases.compute_transforms (params.py:142-180) ----------------------
+ * for the callers outside the render loop (trainer.py:478,485,701; init_utils.py:322).
+ * coefs [G,K] are ALREADY softmaxed (as the reference passes them), ts [B] float frame
+ * coordinates; out [G,B,3,4] = [R | t].  Backward: v_coefs [G,K] overwritten; v_rots [K,T,6],
+ * v_transls [K,T,3], v_ts [B] accumulated (caller zero-fills).                                    */
+int d4_compute_transforms_fwd(const float *coefs, const float *rots, const float *transls, const float *ts,
+                              int G, int K, int T, int B, float *out, d4_stream_t stream);
+int d4_compute_transforms_bwd(const float *coefs, const float *rots, const float *transls, const float *ts,
+                              int G, int K, int T, int B, const float *v_out, float *v_coefs, float *v_rots,
+                              float *v_transls, float *v_ts, d4_stream_t stream);
+
 /* ---- a7: camera sub-exposure pose interpolation ---------------------------------------------
  * replaces MoveModel.forward_start_end_mid's pose part (move_model.py:143-147: pp.se3().Exp(),
  * _interpolate -> spline_utils.linear_interpolation :371-408, .Log(), se3_to_SE3 :204-215).

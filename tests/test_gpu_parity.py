@@ -290,6 +290,21 @@ def test_deform_against_reference_fixtures(fname):
     assert e_m <= 1e-4 and e_q <= 1e-4
     for k, (se, eq) in errs.items():
         assert se <= 1e-4 and eq <= 1e-3, (k, se, eq)
+    # stand-alone compute_transforms (params.py:142-180) against the reference's own output + oracle autograd
+    from deblur4dgs_b200.motion import compute_transforms
+    coefs = torch.softmax(torch.from_numpy(g["in_motion_coefs"]), -1)
+    leaves_c = [x.clone().requires_grad_(True) for x in (coefs, torch.from_numpy(g["in_rots"]), torch.from_numpy(g["in_transls"]))]
+    ts_c = torch.from_numpy(g["transforms_ts"]).float().requires_grad_(True)
+    ref_tf = odef.compute_transforms(ts_c, *leaves_c)
+    leaves_g = [x.detach().to(DEV).requires_grad_(True) for x in leaves_c]
+    ts_g = ts_c.detach().to(DEV).requires_grad_(True)
+    tf = compute_transforms(ts_g, *leaves_g)
+    assert rel_err(tf.detach().cpu().numpy(), g["transforms"]) <= 1e-4
+    v = torch.randn(ref_tf.shape, generator=torch.Generator().manual_seed(1))
+    gr = torch.autograd.grad((ref_tf * v).sum(), leaves_c + [ts_c])
+    (tf * v.to(DEV)).sum().backward()
+    for got, want, nm in zip([x.grad for x in leaves_g] + [ts_g.grad], gr, ["coefs", "rots", "transls", "ts"]):
+        assert scale_err(got.cpu().numpy(), want.numpy()) <= 1e-4, nm
 
 
 def test_deform_large_vs_oracle_and_wrappers():
