@@ -127,6 +127,8 @@ __device__ __forceinline__ void stage_gaussian(const BlendArgs &a, int c, int64_
             if (k < d0) dst[k] = __ldg(col + k);
     }
     if (a.depths) dst[D - 1] = __ldg(a.depths + g);
+#pragma unroll
+    for (int k = D; k < DS; ++k) dst[k] = 0.f;  // pad lanes feed the packed fp32x2 path: keep them finite
 }
 
 // ----------------------------------------------------------------------------- forward
@@ -161,9 +163,12 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
     float T = 1.0f;
     int32_t cur_idx = 0;
     bool done = !inside;
-    float out[D];
+    // accumulators as fp32x2 pairs: Blackwell's FFMA2 retires two fp32 FMAs per issue slot, and this
+    // kernel is bound by issue slots
+    constexpr int D2 = (D + 1) / 2;
+    float2 out2[D2];
 #pragma unroll
-    for (int k = 0; k < D; ++k) out[k] = 0.f;
+    for (int k = 0; k < D2; ++k) out2[k] = make_float2(0.f, 0.f);
 
     for (int b = 0; b < num_batches; ++b) {
         if (__syncthreads_count(done) >= kBlendThreads) break;
@@ -191,17 +196,14 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
                         done = true;
                     } else {
                         const float vis = alpha * T;
+                        const float2 vis2 = make_float2(vis, vis);
                         const float *cp = s_col + t * DS;
 #pragma unroll
-                        for (int k4 = 0; k4 < D / 4; ++k4) {
+                        for (int k4 = 0; k4 < DS / 4; ++k4) {  // DS = D rounded up to 4: the pad lanes are never stored
                             const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
-                            out[4 * k4 + 0] = fmaf(cv.x, vis, out[4 * k4 + 0]);
-                            out[4 * k4 + 1] = fmaf(cv.y, vis, out[4 * k4 + 1]);
-                            out[4 * k4 + 2] = fmaf(cv.z, vis, out[4 * k4 + 2]);
-                            out[4 * k4 + 3] = fmaf(cv.w, vis, out[4 * k4 + 3]);
+                            if (2 * k4 < D2) out2[2 * k4] = __ffma2_rn(make_float2(cv.x, cv.y), vis2, out2[2 * k4]);
+                            if (2 * k4 + 1 < D2) out2[2 * k4 + 1] = __ffma2_rn(make_float2(cv.z, cv.w), vis2, out2[2 * k4 + 1]);
                         }
-#pragma unroll
-                        for (int k = D / 4 * 4; k < D; ++k) out[k] = fmaf(cp[k], vis, out[k]);
                         cur_idx = (int32_t)(batch_start + t);
                         T = next_T;
                     }
@@ -215,6 +217,9 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
     }
 
     // epilogue: background, ED normalisation, coalesced store through shared memory
+    float out[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) out[k] = (k & 1) ? out2[k >> 1].y : out2[k >> 1].x;
     const float alpha_out = 1.0f - T;
     if (a.backgrounds) {
         const int d0 = a.depths ? D - 1 : D;
@@ -326,7 +331,7 @@ struct BwdCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(kBlendThreads, 3)
+__global__ void __launch_bounds__(kBlendThreads, 4)
 blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
                  const float *__restrict__ acc_depth, const float *__restrict__ v_render_colors,
                  const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
@@ -394,6 +399,11 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
         for (int k = 0; k < D; ++k)
             if (k < d0) bgdot = fmaf(__ldg(a.backgrounds + (int64_t)c * a.D0 + k), v_out[k], bgdot);
     }
+    // v_out as fp32x2 pairs for the packed FFMA2 / FMUL2 path (pad lane zero; smem colour pads are finite)
+    constexpr int D2 = (D + 1) / 2;
+    float2 v2[D2];
+#pragma unroll
+    for (int k2 = 0; k2 < D2; ++k2) v2[k2] = make_float2(v_out[2 * k2], (2 * k2 + 1 < D) ? v_out[2 * k2 + 1] : 0.f);
     // constant part of dL/dalpha_i * (1 - alpha_i):  T_final * (v_alpha_out - bg.v_out)
     const float tail = T_final * (v_ra - bgdot);
     float T = T_final;
@@ -532,20 +542,26 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
                     fac = alpha * T;
                     // s = <c_g, v_out>, four independent partial sums (short dependency chain)
                     const float *cp = s_col + t * DS;
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k4 = 0; k4 < D / 4; ++k4) {
+                    for (int k4 = 0; k4 < DS / 4; ++k4) {  // pad lanes of v2 are zero
                         const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
-                        s0 = fmaf(cv.x, v_out[4 * k4 + 0], s0);
-                        s1 = fmaf(cv.y, v_out[4 * k4 + 1], s1);
-                        s2 = fmaf(cv.z, v_out[4 * k4 + 2], s2);
-                        s3 = fmaf(cv.w, v_out[4 * k4 + 3], s3);
+                        if (2 * k4 < D2) sa = __ffma2_rn(make_float2(cv.x, cv.y), v2[2 * k4], sa);
+                        if (2 * k4 + 1 < D2) sb = __ffma2_rn(make_float2(cv.z, cv.w), v2[2 * k4 + 1], sb);
                     }
+                    const float s = (sa.x + sa.y) + (sb.x + sb.y);
+                    if constexpr (DM == 0) {
+                        const float2 fac2 = make_float2(fac, fac);
 #pragma unroll
-                    for (int k = D / 4 * 4; k < D; ++k) s0 = fmaf(cp[k], v_out[k], s0);
-                    const float s = (s0 + s1) + (s2 + s3);
+                        for (int k2 = 0; k2 < D2; ++k2) {
+                            const float2 p = __fmul2_rn(fac2, v2[k2]);
+                            r[2 * k2] = p.x;
+                            if (2 * k2 + 1 < D) r[2 * k2 + 1] = p.y;
+                        }
+                    } else {
 #pragma unroll
-                    for (int k = DM; k < D; ++k) r[k - DM] = fac * v_out[k];  // channels not on the MMA path
+                        for (int k = DM; k < D; ++k) r[k - DM] = fac * v_out[k];  // channels not on the MMA path
+                    }
                     const float v_alpha = s * T - (S - tail) * ra;
                     S = fmaf(s, fac, S);
                     if (araw <= kAlphaMax) {
