@@ -77,9 +77,49 @@ combine_bwd_kernel(const float *__restrict__ imgs, int N, int64_t P, int D, int 
     for (int n = 0; n < N; ++n) v_imgs[n * PD + e] = mean_wins ? v * invN : (n == arg ? v : 0.f);
 }
 
+// Row f3: densification statistics (flow3d/trainer.py:953-990, Trainer._prepare_control_step).
+// The reference runs, per sub-exposure render, ~10 launches (where / clone / scale / norm / 2x index_add /
+// index_select / maximum / index_put) over [G]; here one thread per Gaussian walks all N renders:
+// N*G*12 B read, no atomics, same accumulation order as the reference's loop over ii.
+__global__ void __launch_bounds__(256)
+densify_stats_kernel(const float *__restrict__ v_means2d, const int32_t *__restrict__ radii, int N, int G, float sx,
+                     float sy, float inv_max_wh, float *__restrict__ grad_norm_acc, int64_t *__restrict__ vis_count,
+                     float *__restrict__ max_radii) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    float acc = grad_norm_acc[g];
+    int64_t cnt = vis_count[g];
+    float mr = max_radii ? max_radii[g] : 0.f;
+    for (int n = 0; n < N; ++n) {
+        const int64_t idx = (int64_t)n * G + g;
+        const int32_t r = __ldg(radii + idx);
+        if (r <= 0) continue;
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(v_means2d) + idx);
+        const float gx = v.x * sx, gy = v.y * sy;
+        acc += sqrtf(gx * gx + gy * gy);
+        cnt += 1;
+        mr = fmaxf(mr, (float)r * inv_max_wh);
+    }
+    grad_norm_acc[g] = acc;
+    vis_count[g] = cnt;
+    if (max_radii) max_radii[g] = mr;
+}
+
 }  // namespace d4
 
 using namespace d4;
+
+extern "C" int d4_densify_stats(const float *v_means2d, const int32_t *radii, int N, int G, float sx, float sy,
+                                float inv_max_wh, float *grad_norm_acc, int64_t *vis_count, float *max_radii,
+                                d4_stream_t stream) {
+    D4_CHECK_ARG(N >= 1 && G >= 0 && grad_norm_acc && vis_count, "d4_densify_stats: bad arguments");
+    if (G == 0) return 0;
+    D4_CHECK_ARG(v_means2d && radii && ((uintptr_t)v_means2d & 7) == 0, "d4_densify_stats: null/unaligned pointer");
+    densify_stats_kernel<<<cdiv(G, 256), 256, 0, as_stream(stream)>>>(v_means2d, radii, N, G, sx, sy, inv_max_wh,
+                                                                     grad_norm_acc, vis_count, max_radii);
+    D4_CHECK_LAUNCH("d4_densify_stats");
+    return 0;
+}
 
 extern "C" int d4_combine_fwd(const float *imgs, const float *alphas, int N, int64_t P, int D, int max_ch, int min_ch,
                               int ref_quirk, float *out_img, float *out_alpha, d4_stream_t stream) {

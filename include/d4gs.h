@@ -207,6 +207,18 @@ int d4_combine_bwd(const float *imgs, int N, int64_t P, int D, int max_ch, int m
                    const float *v_out_img, const float *v_out_alpha, float *v_imgs, float *v_alphas,
                    d4_stream_t stream);
 
+/* ---- f3 ("next" row): densification statistics --------------------------------------------------
+ * replaces Trainer._prepare_control_step's per-render loop (flow3d/trainer.py:967-989) for the N
+ * sub-exposure renders of one frame: for every Gaussian visible in render n (radii > 0)
+ *   grad_norm_acc[g] += |(v_means2d.x * sx, v_means2d.y * sy)|,  vis_count[g] += 1,
+ *   max_radii[g] = max(max_radii[g], radii / max(W,H))   (max_radii may be NULL: the reference's
+ *   non-in-place index_put at trainer.py:989 discards that update).
+ * v_means2d [N,G,2] (the .grad of meta["means2d"]), radii i32 [N,G]; sx = W/2 * batch * N,
+ * sy = H/2 * batch * N (trainer.py:976-977).                                                       */
+int d4_densify_stats(const float *v_means2d, const int32_t *radii, int N, int G, float sx, float sy,
+                     float inv_max_wh, float *grad_norm_acc, int64_t *vis_count, float *max_radii,
+                     d4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

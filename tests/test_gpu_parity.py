@@ -476,3 +476,32 @@ def test_bucket_binning_equals_radix_binning():
         bin_tiles(means2d, radii, depths, 16, 1, 1, tpg, method="bucket")
     ids, fl, off = bin_tiles(means2d, radii, depths, 16, 1, 1, tpg, method="auto")
     assert ids.numel() == G and bool((ids[1:] >= ids[:-1]).all())
+
+
+def test_densify_stats_f3():
+    """Row f3: Trainer._prepare_control_step's per-render loop (trainer.py:967-989) restated literally in torch."""
+    from deblur4dgs_b200.control import accumulate_densify_stats
+    g = torch.Generator().manual_seed(2)
+    N, G, W, H, B = 5, 7001, 512, 288, 2
+    grads = torch.randn(N, 1, G, 2, generator=g).to(DEV) * 1e-4
+    radii = (torch.rand(N, 1, G, generator=g) * 30 - 8).clamp_min(0).int().to(DEV)
+    ref = {"xys_grad_norm_acc": torch.rand(G, generator=g).to(DEV), "vis_count": torch.randint(0, 5, (G,), generator=g).to(DEV),
+           "max_radii": torch.rand(G, generator=g).to(DEV) * 0.01}
+    got = {k: v.clone() for k, v in ref.items()}
+    exp_max = ref["max_radii"].clone()
+    for ii in range(N):  # literal reference loop
+        sel = radii[ii] > 0
+        gidcs = torch.where(sel)[1]
+        xys_grad = grads[ii].clone()
+        xys_grad[..., 0] *= W / 2.0 * B * N
+        xys_grad[..., 1] *= H / 2.0 * B * N
+        ref["xys_grad_norm_acc"].index_add_(0, gidcs, xys_grad[sel].norm(dim=-1))
+        ref["vis_count"].index_add_(0, gidcs, torch.ones_like(gidcs, dtype=torch.int64))
+        max_radii = torch.maximum(ref["max_radii"].index_select(0, gidcs), radii[ii][sel] / max(W, H))
+        ref["max_radii"].index_put((gidcs,), max_radii)  # not in place: discarded, as in the reference
+        exp_max[gidcs] = torch.maximum(exp_max[gidcs], radii[ii][sel] / max(W, H))
+    accumulate_densify_stats(got, grads[:, 0], radii[:, 0], (W, H), batch_size=B)
+    assert torch.allclose(got["xys_grad_norm_acc"], ref["xys_grad_norm_acc"], rtol=1e-5, atol=1e-7)
+    assert torch.equal(got["vis_count"], ref["vis_count"]) and torch.equal(got["max_radii"], ref["max_radii"])
+    accumulate_densify_stats(got, grads[:, 0], radii[:, 0], (W, H), batch_size=B, update_max_radii=True)
+    assert torch.allclose(got["max_radii"], exp_max)
