@@ -284,7 +284,8 @@ def main():
     launches_per_step = sum(len(v) * _cabi.LAUNCHES.get(k, 1) for k, v in prof.items()) / args.steps
     n_sort_passes = math.ceil((32 + _cabi.lib().d4_tile_n_bits(math.ceil(W / 16) * math.ceil(H / 16)) +
                                int(math.floor(math.log2(frames_per_step_local))) + 1) / 8)
-    launches_per_step += (3 * n_sort_passes - 1)  # d4_sort_pairs_u64 launches 3 kernels per pass
+    if "d4_sort_pairs_u64" in prof:  # radix fallback only: 3 kernels per pass (the default bucketed binning has none)
+        launches_per_step += (3 * n_sort_passes - 1) * len(prof["d4_sort_pairs_u64"]) / args.steps
 
     # ---- timed region 2: end to end through the public API with HOST buffers --------------
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
