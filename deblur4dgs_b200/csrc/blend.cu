@@ -180,40 +180,48 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
         __syncthreads();
         const int batch_size = (int)min((int64_t)kBatch, range_end - batch_start);
         bool warp_done = __all_sync(0xffffffffu, done);
+        // one Gaussian of the hit list for this pixel; returns true when the whole warp is finished
+        auto composite = [&](int t, float power, float L) -> bool {
+            const float alpha = fminf(kAlphaMax, ex2_approx(power));
+            const bool valid = !done && power <= L && alpha >= kAlphaMin;
+            if (!__any_sync(0xffffffffu, valid)) return false;
+            if (valid) {
+                const float next_T = T * (1.0f - alpha);
+                if (next_T <= kTMin) {
+                    done = true;
+                } else {
+                    const float vis = alpha * T;
+                    const float2 vis2 = make_float2(vis, vis);
+                    const float *cp = s_col + t * DS;
+#pragma unroll
+                    for (int k4 = 0; k4 < DS / 4; ++k4) {  // DS = D rounded up to 4: the pad lanes are never stored
+                        const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
+                        if (2 * k4 < D2) out2[2 * k4] = __ffma2_rn(make_float2(cv.x, cv.y), vis2, out2[2 * k4]);
+                        if (2 * k4 + 1 < D2) out2[2 * k4 + 1] = __ffma2_rn(make_float2(cv.z, cv.w), vis2, out2[2 * k4 + 1]);
+                    }
+                    cur_idx = (int32_t)(batch_start + t);
+                    T = next_T;
+                }
+            }
+            return __all_sync(0xffffffffu, done);
+        };
         for (int chunk = 0; chunk * 32 < batch_size && !warp_done; ++chunk) {
             uint32_t bits = __ballot_sync(0xffffffffu, (s_mask[chunk * 32 + lane] >> w) & 1u);
             while (bits) {
-                const int t = chunk * 32 + __ffs(bits) - 1;
+                // two hits per trip: both exponents are evaluated before either is composited (ILP for the
+                // LDS -> FMA -> MUFU chain, which is what the issue slots were waiting on)
+                const int ta = chunk * 32 + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const float4 g0 = s_geom[t];
-                const float4 cn = s_conic[t];
-                const float dx = g0.x - px, dy = g0.y - py;
-                const float power = fmaf(cn.z * dy, dy, fmaf(fmaf(cn.y, dy, cn.x * dx), dx, g0.z));
-                const float alpha = fminf(kAlphaMax, ex2_approx(power));
-                const bool valid = !done && power <= g0.z && alpha >= kAlphaMin;
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                if (valid) {
-                    const float next_T = T * (1.0f - alpha);
-                    if (next_T <= kTMin) {
-                        done = true;
-                    } else {
-                        const float vis = alpha * T;
-                        const float2 vis2 = make_float2(vis, vis);
-                        const float *cp = s_col + t * DS;
-#pragma unroll
-                        for (int k4 = 0; k4 < DS / 4; ++k4) {  // DS = D rounded up to 4: the pad lanes are never stored
-                            const float4 cv = *reinterpret_cast<const float4 *>(cp + 4 * k4);
-                            if (2 * k4 < D2) out2[2 * k4] = __ffma2_rn(make_float2(cv.x, cv.y), vis2, out2[2 * k4]);
-                            if (2 * k4 + 1 < D2) out2[2 * k4 + 1] = __ffma2_rn(make_float2(cv.z, cv.w), vis2, out2[2 * k4 + 1]);
-                        }
-                        cur_idx = (int32_t)(batch_start + t);
-                        T = next_T;
-                    }
-                }
-                if (__all_sync(0xffffffffu, done)) {
-                    warp_done = true;
-                    break;
-                }
+                const bool has_b = bits != 0u;
+                const int tb = has_b ? chunk * 32 + __ffs(bits) - 1 : ta;
+                bits &= bits - 1;  // no-op when bits == 0
+                const float4 ga = s_geom[ta], ca = s_conic[ta];
+                const float4 gb = s_geom[tb], cb = s_conic[tb];
+                const float dxa = ga.x - px, dya = ga.y - py, dxb = gb.x - px, dyb = gb.y - py;
+                const float pa = fmaf(ca.z * dya, dya, fmaf(fmaf(ca.y, dya, ca.x * dxa), dxa, ga.z));
+                const float pb = fmaf(cb.z * dyb, dyb, fmaf(fmaf(cb.y, dyb, cb.x * dxb), dxb, gb.z));
+                if (composite(ta, pa, ga.z)) { warp_done = true; break; }
+                if (has_b && composite(tb, pb, gb.z)) { warp_done = true; break; }
             }
         }
     }
@@ -244,13 +252,26 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
         for (int k = 0; k < D; ++k) dst[k] = out[k];
     }
     __syncthreads();
-    const int row_elems = kTile * D;
-    for (int e = tid; e < kTile * row_elems; e += kBlendThreads) {
-        const int r = e / row_elems, col = e - r * row_elems;
+    // every tile row is one contiguous run of 16*D floats in the channels-last image: thread `tid` owns column
+    // positions tid, tid + 256, ... of that run (pixel / channel split computed once, not per element)
+    constexpr int row_elems = kTile * D;
+    constexpr int kCols = (row_elems + kBlendThreads - 1) / kBlendThreads;
+    int src_off[kCols];
+    bool col_ok[kCols];
+#pragma unroll
+    for (int q = 0; q < kCols; ++q) {
+        const int col = tid + q * kBlendThreads;
         const int pxl = col / D, k = col - pxl * D;
-        const int gi = ty * kTile + r, gj = tx * kTile + pxl;
-        if (gi < a.height && gj < a.width)
-            render_colors[(((int64_t)c * a.height + gi) * a.width + gj) * D + k] = s_col[(r * kTile + pxl) * DP + k];
+        src_off[q] = pxl * DP + k;
+        col_ok[q] = col < row_elems && (tx * kTile + pxl) < a.width;
+    }
+    const int rows = min(kTile, a.height - ty * kTile);
+    float *dst_row = render_colors + (((int64_t)c * a.height + ty * kTile) * a.width + tx * kTile) * D + tid;
+    for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int q = 0; q < kCols; ++q)
+            if (col_ok[q]) dst_row[q * kBlendThreads] = s_col[r * kTile * DP + src_off[q]];
+        dst_row += (int64_t)a.width * D;
     }
 }
 
