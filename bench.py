@@ -37,7 +37,7 @@ import torch  # noqa: E402
 
 METRIC = "rendered sub-exposure frames/sec at 720x1280, 300k Gaussians (fwd+bwd)"
 UNIT = "frames/s"
-D0 = 16  # rgb(3) + fg mask(1) + 4x3 track channels; +1 expected depth => D = 17 (scene_model.py:205-296)
+D0_SYNTH = 16  # rgb(3) + fg mask(1) + 4x3 track channels; +1 expected depth => D = 17 (scene_model.py:205-296)
 
 
 def peaks():
@@ -145,11 +145,11 @@ def run_reference_arm(args):
     orc.set_num_threads(cores)
     sc = make_config(args.config)
     for _ in range(min(args.warmup, 1)):
-        cpu_frame(sc, D0, 0)
+        cpu_frame(sc, D0_SYNTH, 0)
     ts = []
     steps = max(1, args.steps)
     for k in range(steps):
-        dt, n_isects = cpu_frame(sc, D0, k % sc.N)
+        dt, n_isects = cpu_frame(sc, D0_SYNTH, k % sc.N)
         ts.append(dt)
     total = sum(ts)
     value = steps / total
@@ -165,8 +165,10 @@ def run_reference_arm(args):
 
 
 def workload_config(args, sc):
-    return {"workload": f"{args.config}: {sc.width}x{sc.height}, G={sc.G} (fg {sc.num_fg}), K={sc.rots.shape[0]}, "
-                        f"N={sc.N} sub-exposures, D={D0 + 1} channels (RGB+ED), fwd+bwd",
+    d0 = 4 + sc.extra_channels.shape[1]
+    name = args.config if not getattr(args, "checkpoint", None) else f"checkpoint {os.path.basename(args.checkpoint)}"
+    return {"workload": f"{name}: {sc.width}x{sc.height}, G={sc.G} (fg {sc.num_fg}), K={sc.rots.shape[0]}, "
+                        f"N={sc.N} sub-exposures, D={d0 + 1} channels (RGB+ED), fwd+bwd",
             "shard": args.shard, "l2": "per-step working set (N x H x W x D image stack, 564 MB at c3) exceeds the 126 MB L2"}
 
 
@@ -182,6 +184,11 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--shard", default="frames", choices=["frames", "subexposures"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--checkpoint", default=None, help="replay a reference checkpoint (trainer.py:126-140) instead of "
+                                                       "the synthetic scene; --width/--height/--frame select the view")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--frame", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -190,7 +197,7 @@ def main():
     import torch.distributed as dist
     from deblur4dgs_b200 import _cabi
     from deblur4dgs_b200.parallel import allreduce_sum_, render_frame_sharded, shard_indices
-    from deblur4dgs_b200.scene import render_subexposures
+    from deblur4dgs_b200.scene import assemble_gaussians, render_subexposures
     from deblur4dgs_b200.synthetic import CONFIGS, make_config
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,7 +214,14 @@ def main():
 
     # every rank gets its own frame in "frames" mode (different seed offset => different view/time)
     G, W, H, K, N, seed = CONFIGS[args.config]
-    sc_cpu = make_config(args.config, seed=seed + (rank if args.shard == "frames" else 0))
+    if args.checkpoint:
+        from deblur4dgs_b200.checkpoint import load_checkpoint
+        W, H = args.width or W, args.height or H
+        sc_cpu, _ = load_checkpoint(args.checkpoint, W, H, frame=args.frame, N=N)
+        G, K = sc_cpu.G, sc_cpu.rots.shape[0]
+    else:
+        sc_cpu = make_config(args.config, seed=seed + (rank if args.shard == "frames" else 0))
+    D0 = 4 + sc_cpu.extra_channels.shape[1]  # rgb + fg mask + track channels
     host = {k: v.pin_memory() for k, v in sc_cpu.tensors().items()}
     sc = sc_cpu.to(dev)
     P = W * H
@@ -222,12 +236,11 @@ def main():
     def step(scn, want_outputs=False):
         """One blurry frame forward + backward from the raw scene parameters."""
         p = {k: getattr(scn, k).detach().requires_grad_(True) for k in param_names}
-        scales = torch.exp(torch.cat([p["fg_scales"], p["bg_scales"]], 0))
-        opac = torch.sigmoid(torch.cat([p["fg_opacities"], p["bg_opacities"]], 0))
-        rgb = torch.sigmoid(torch.cat([p["fg_colors"], p["bg_colors"]], 0))
-        mask = torch.zeros(scn.G, 1, device=dev)
-        mask[: scn.num_fg] = 1.0
-        colors = torch.cat([rgb, mask, scn.extra_channels], dim=-1)
+        # activations + fg|bg concat + [rgb | fg mask | track channels] feature vector (row f1), one kernel
+        scales, opac, colors = assemble_gaussians(p["fg_scales"], p["bg_scales"], p["fg_opacities"], p["bg_opacities"],
+                                                  p["fg_colors"], p["bg_colors"],
+                                                  extra=scn.extra_channels if scn.extra_channels.shape[1] else None,
+                                                  with_mask=True)
 
         def local(times, RTs, combine):
             return render_subexposures(p["fg_means"], p["fg_quats"], p["motion_coefs"], p["bg_means"], p["bg_quats"],
@@ -381,7 +394,7 @@ def main():
             orc.set_num_threads(cores)
             cpu_frame(sc_cpu, D0, 0)  # warm-up (page-in, OpenMP pool)
             n_cpu = 2
-            dts = [cpu_frame(sc_cpu, D0, i)[0] for i in range(n_cpu)]
+            dts = [cpu_frame(sc_cpu, D0, i % sc_cpu.N)[0] for i in range(n_cpu)]
             line["cpu_baseline"] = {"value": n_cpu / sum(dts), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_cpu} sub-exposure frames fwd+bwd of {args.config} (1 warm-up), oracle port "
                                               "(torch-CPU deformation + C/OpenMP rasterizer), all host cores"}

@@ -29,6 +29,7 @@ UNITS = {
     "deform.cu": [],
     "combine.cu": [],
     "camera.cu": [],
+    "assemble.cu": [],
 }
 HEADERS = ["common.cuh", "project_math.cuh", "deform_math.cuh", "camera_math.cuh",
            os.path.join("..", "..", "include", "d4gs.h")]

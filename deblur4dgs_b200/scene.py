@@ -102,3 +102,49 @@ def render_subexposures(
         else:
             out["img"], out["acc"] = imgs, alphas
     return out
+
+
+class _Assemble(torch.autograd.Function):
+    """Row f1: activations + fg|bg concat + [rgb | mask | extra] feature vector in one pass."""
+
+    @staticmethod
+    def forward(ctx, fg_scales, bg_scales, fg_opac, bg_opac, fg_colors, bg_colors, extra, with_mask):
+        c = lambda t: None if t is None else t.float().contiguous()
+        fg_scales, bg_scales, fg_opac, bg_opac, fg_colors, bg_colors, extra = map(
+            c, (fg_scales, bg_scales, fg_opac, bg_opac, fg_colors, bg_colors, extra))
+        Gf = fg_scales.shape[0]
+        Gb = 0 if bg_scales is None else bg_scales.shape[0]
+        E = 0 if extra is None else extra.shape[1]
+        G, dev = Gf + Gb, fg_scales.device
+        D0 = 3 + int(with_mask) + E
+        scales = torch.empty((G, 3), dtype=torch.float32, device=dev)
+        opac = torch.empty((G,), dtype=torch.float32, device=dev)
+        colors = torch.empty((G, D0), dtype=torch.float32, device=dev)
+        call("d4_assemble_fwd", ptr(fg_scales), ptr(bg_scales), ptr(fg_opac), ptr(bg_opac), ptr(fg_colors),
+             ptr(bg_colors), ptr(extra) if E else None, Gf, Gb, E, int(with_mask), ptr(scales), ptr(opac), ptr(colors),
+             stream_ptr())
+        ctx.save_for_backward(scales, opac, colors)
+        ctx.cfg = (Gf, Gb, E, int(with_mask), extra is not None and E > 0)
+        return scales, opac, colors
+
+    @staticmethod
+    def backward(ctx, v_scales, v_opac, v_colors):
+        scales, opac, colors = ctx.saved_tensors
+        Gf, Gb, E, with_mask, has_extra = ctx.cfg
+        dev = scales.device
+        z = lambda t, ref: torch.zeros_like(ref) if t is None else t.float().contiguous()
+        v_scales, v_opac, v_colors = z(v_scales, scales), z(v_opac, opac), z(v_colors, colors)
+        mk = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        vfs, vfo, vfc = mk(Gf, 3), mk(Gf), mk(Gf, 3)
+        vbs, vbo, vbc = (mk(Gb, 3), mk(Gb), mk(Gb, 3)) if Gb else (None, None, None)
+        vex = mk(Gf + Gb, E) if has_extra else None
+        call("d4_assemble_bwd", ptr(scales), ptr(opac), ptr(colors), ptr(v_scales), ptr(v_opac), ptr(v_colors), Gf, Gb,
+             E, with_mask, ptr(vfs), ptr(vbs), ptr(vfo), ptr(vbo), ptr(vfc), ptr(vbc), ptr(vex), stream_ptr())
+        return vfs, vbs, vfo, vbo, vfc, vbc, vex, None
+
+
+def assemble_gaussians(fg_scales, bg_scales, fg_opacities, bg_opacities, fg_colors, bg_colors,
+                       extra: Optional[Tensor] = None, with_mask: bool = True):
+    """Raw (pre-activation) fg / bg parameters -> (scales [G,3], opacities [G], colors [G, 3(+1)+E]) as
+    SceneModel.render assembles them (params.py:70-84, scene_model.py:122-143, 205-289).  bg_* may be None."""
+    return _Assemble.apply(fg_scales, bg_scales, fg_opacities, bg_opacities, fg_colors, bg_colors, extra, bool(with_mask))

@@ -207,6 +207,20 @@ int d4_combine_bwd(const float *imgs, int N, int64_t P, int D, int max_ch, int m
                    const float *v_out_img, const float *v_out_alpha, float *v_imgs, float *v_alphas,
                    d4_stream_t stream);
 
+/* ---- f1 ("next" row): activations + fg|bg concatenation + feature-vector assembly ------------------
+ * replaces GaussianParams' activations (params.py:39-43, 70-84: exp / sigmoid / sigmoid), the fg|bg
+ * torch.cat of SceneModel.get_*_all (scene_model.py:122-143) and the colors_override assembly
+ * [rgb | fg mask | extra track channels] (scene_model.py:205-289) with one pass per render call.
+ * raw fg_* [Gf,.], bg_* [Gb,.], extra [G,E] or NULL (E = 0); out: scales [G,3], opac [G],
+ * colors [G, 3 + (with_mask ? 1 : 0) + E].  Backward overwrites every v_* output (v_extra may be NULL). */
+int d4_assemble_fwd(const float *fg_scales, const float *bg_scales, const float *fg_opac, const float *bg_opac,
+                    const float *fg_colors, const float *bg_colors, const float *extra, int Gf, int Gb, int E,
+                    int with_mask, float *scales, float *opac, float *colors, d4_stream_t stream);
+int d4_assemble_bwd(const float *scales, const float *opac, const float *colors, const float *v_scales,
+                    const float *v_opac, const float *v_colors, int Gf, int Gb, int E, int with_mask,
+                    float *v_fg_scales, float *v_bg_scales, float *v_fg_opac, float *v_bg_opac,
+                    float *v_fg_colors, float *v_bg_colors, float *v_extra, d4_stream_t stream);
+
 /* ---- f3 ("next" row): densification statistics --------------------------------------------------
  * replaces Trainer._prepare_control_step's per-render loop (flow3d/trainer.py:967-989) for the N
  * sub-exposure renders of one frame: for every Gaussian visible in render n (radii > 0)

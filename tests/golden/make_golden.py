@@ -164,9 +164,34 @@ def camera_golden():
     print("wrote camera_se3.npz", tuple(Rt.shape))
 
 
+def checkpoint_golden():
+    """A checkpoint in the reference's own on-disk layout (trainer.py:126-140): the state dicts come from
+    the reference's GaussianParams / MotionBases modules, nested exactly as SceneModel registers them
+    (scene_model.py:24-30: fg, motion_bases, bg, buffers bg_scene_scale / Ks / w2cs)."""
+    GaussianParams, MotionBases, _ = _import_reference()
+    sc = make_scene(G=900, width=96, height=64, K=5, N=3, seed=31)
+    fg = GaussianParams(sc.fg_means, sc.fg_quats, sc.fg_scales, sc.fg_colors, sc.fg_opacities, motion_coefs=sc.motion_coefs)
+    bg = GaussianParams(sc.bg_means, sc.bg_quats, sc.bg_scales, sc.bg_colors, sc.bg_opacities, scene_scale=1.3)
+    mb = MotionBases(sc.rots, sc.transls)
+    T = sc.rots.shape[1]
+    sd = {}
+    sd.update({"fg." + k: v.detach().clone() for k, v in fg.state_dict().items()})
+    sd.update({"motion_bases." + k: v.detach().clone() for k, v in mb.state_dict().items()})
+    sd.update({"bg." + k: v.detach().clone() for k, v in bg.state_dict().items()})
+    sd["bg_scene_scale"] = torch.tensor(1.3)
+    sd["Ks"] = sc.K.repeat(T, 1, 1)
+    w2cs = sc.w2c.repeat(T, 1, 1).clone()
+    w2cs[:, 0, 3] = torch.linspace(-0.1, 0.1, T)
+    sd["w2cs"] = w2cs
+    torch.save({"model": sd, "optimizers": {}, "schedulers": {}, "global_step": 1234, "epoch": 7,
+                "move_model": {"time_params": torch.full((1, 8), 0.5)}}, os.path.join(HERE, "ckpt_small.pt"))
+    print("wrote ckpt_small.pt", sorted(sd.keys()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     camera_golden()
+    checkpoint_golden()
     deform_golden("k6_n5", G=600, K=6, N=5, seed=11)
     deform_golden("k10_n9", G=900, K=10, N=9, seed=12)
     deform_golden("k3_n1_int", G=257, K=3, N=1, seed=13, int_ts=True)

@@ -83,3 +83,24 @@ def test_synthetic_configs_match_baseline():
     sc2 = make_scene(G=1000, width=64, height=48, K=5, N=4, seed=3)
     assert torch.equal(sc.fg_means, sc2.fg_means) and sc.num_fg == 300 and sc.colors_all(16).shape == (1000, 16)
     assert sc.times.shape == (4,) and sc.RTs.shape == (4, 3, 4)
+
+
+def test_checkpoint_loader_reads_reference_layout():
+    """Row f2: tests/golden/ckpt_small.pt was written with the reference's own GaussianParams / MotionBases
+    state dicts in Trainer.save_checkpoint's layout (tests/golden/make_golden.py)."""
+    from deblur4dgs_b200.checkpoint import load_checkpoint, scene_from_state_dict, scene_to_state_dict
+    from deblur4dgs_b200.synthetic import make_scene
+    path = os.path.join(ROOT, "tests", "golden", "ckpt_small.pt")
+    sc, extras = load_checkpoint(path, 96, 64, frame=2, N=5)
+    ref = make_scene(G=900, width=96, height=64, K=5, N=3, seed=31)
+    for k in ["fg_means", "fg_quats", "fg_scales", "fg_colors", "fg_opacities", "motion_coefs", "bg_means", "bg_quats",
+              "bg_scales", "bg_colors", "bg_opacities", "rots", "transls"]:
+        assert torch.equal(getattr(sc, k), getattr(ref, k)), k
+    assert extras["global_step"] == 1234 and extras["epoch"] == 7
+    assert sc.w2c.shape == (1, 4, 4) and abs(float(sc.w2c[0, 0, 3]) - (-0.1 + 0.2 * 2 / 7)) < 1e-6
+    assert sc.times.shape == (5,) and abs(float(sc.times[0]) - 1.5) < 1e-6 and sc.RTs.shape == (5, 3, 4)
+    sd = scene_to_state_dict(sc)
+    sc2 = scene_from_state_dict(sd, 96, 64, frame=0, N=1)
+    assert torch.equal(sc2.fg_means, sc.fg_means) and sc2.num_bg == sc.num_bg
+    with pytest.raises(KeyError):
+        scene_from_state_dict({"fg.params.means": torch.zeros(1, 3)}, 8, 8)

@@ -505,3 +505,32 @@ def test_densify_stats_f3():
     assert torch.equal(got["vis_count"], ref["vis_count"]) and torch.equal(got["max_radii"], ref["max_radii"])
     accumulate_densify_stats(got, grads[:, 0], radii[:, 0], (W, H), batch_size=B, update_max_radii=True)
     assert torch.allclose(got["max_radii"], exp_max)
+
+
+def test_assemble_gaussians_f1():
+    """Row f1: activations + fg|bg cat + feature vector vs the torch expressions of the reference."""
+    from deblur4dgs_b200.scene import assemble_gaussians
+    sc = make_scene(G=5003, width=64, height=48, K=4, N=1, seed=17).to(DEV)
+    for E, with_mask in [(12, True), (0, True), (0, False)]:
+        names = ["fg_scales", "bg_scales", "fg_opacities", "bg_opacities", "fg_colors", "bg_colors"]
+        a = [getattr(sc, n).clone().requires_grad_(True) for n in names]
+        b = [getattr(sc, n).clone().requires_grad_(True) for n in names]
+        ex_a = sc.extra_channels[:, :E].clone().requires_grad_(True) if E else None
+        ex_b = sc.extra_channels[:, :E].clone().requires_grad_(True) if E else None
+        s1, o1, c1 = assemble_gaussians(*a, extra=ex_a, with_mask=with_mask)
+        s2 = torch.exp(torch.cat([b[0], b[1]], 0))
+        o2 = torch.sigmoid(torch.cat([b[2], b[3]], 0))
+        parts = [torch.sigmoid(torch.cat([b[4], b[5]], 0))]
+        if with_mask:
+            m = torch.zeros(sc.G, 1, device=DEV); m[: sc.num_fg] = 1.0
+            parts.append(m)
+        if E:
+            parts.append(ex_b)
+        c2 = torch.cat(parts, -1)
+        assert torch.allclose(s1, s2, rtol=1e-6) and torch.allclose(o1, o2, rtol=1e-6, atol=1e-7) and torch.allclose(c1, c2, rtol=1e-6, atol=1e-7)
+        g = torch.Generator().manual_seed(E)
+        vs, vo, vc = (torch.randn(t.shape, generator=g).to(DEV) for t in (s1, o1, c1))
+        ((s1 * vs).sum() + (o1 * vo).sum() + (c1 * vc).sum()).backward()
+        ((s2 * vs).sum() + (o2 * vo).sum() + (c2 * vc).sum()).backward()
+        for x, y in zip(a + ([ex_a] if E else []), b + ([ex_b] if E else [])):
+            assert torch.allclose(x.grad, y.grad, rtol=1e-5, atol=1e-7)
