@@ -104,3 +104,21 @@ def test_checkpoint_loader_reads_reference_layout():
     assert torch.equal(sc2.fg_means, sc.fg_means) and sc2.num_bg == sc.num_bg
     with pytest.raises(KeyError):
         scene_from_state_dict({"fg.params.means": torch.zeros(1, 3)}, 8, 8)
+
+
+def test_bench_reference_arm_json_contract():
+    """bench.py --impl reference runs on the CPU (oracle port) and prints one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c1",
+                          "--steps", "1", "--warmup", "1", "--gpus", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ["impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"]:
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
