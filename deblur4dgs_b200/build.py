@@ -26,12 +26,13 @@ UNITS = {
     "project.cu": ["-fmad=false"],
     "binning.cu": [],
     "blend.cu": [],
+    "blend_bwd_gp.cu": [],
     "deform.cu": [],
     "combine.cu": [],
     "camera.cu": [],
     "assemble.cu": [],
 }
-HEADERS = ["common.cuh", "project_math.cuh", "deform_math.cuh", "camera_math.cuh",
+HEADERS = ["common.cuh", "blend_common.cuh", "project_math.cuh", "deform_math.cuh", "camera_math.cuh",
            os.path.join("..", "..", "include", "d4gs.h")]
 
 

@@ -21,117 +21,9 @@
 //
 // These kernels are bound by fp32 issue + MUFU.EX2 + shuffle throughput, not by
 // HBM: algorithmic bytes per (pixel, Gaussian) pair are ~0.4.
-#include <stdlib.h>
-
-#include "common.cuh"
+#include "blend_common.cuh"
 
 namespace d4 {
-
-constexpr int kTile = 16;
-constexpr int kBlendThreads = kTile * kTile;
-constexpr int kBatch = kBlendThreads;
-
-template <int D>
-struct BlendCfg {
-    static constexpr int DS = (D + 3) / 4 * 4;  // smem colour stride (float4 aligned)
-    static constexpr int DP = D | 1;            // odd stride for conflict-free per-pixel staging
-    static constexpr int V = D + 6;             // per-Gaussian gradient values
-};
-
-struct BlendArgs {
-    const float *means2d, *conics, *opacities, *colors, *depths, *backgrounds;
-    int64_t colors_cs;
-    int C, G, D0, width, height, tile_w, tile_h;
-    const int32_t *tile_offsets, *flatten_ids;
-    int64_t n_isects;
-    int normalize_depth;
-};
-
-// pixel owned by this thread: warp w -> 8x4 block (w&1, w>>1), lane -> (lane&7, lane>>3)
-__device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
-    int w = tid >> 5, lane = tid & 31;
-    lx = (w & 1) * 8 + (lane & 7);
-    ly = (w >> 1) * 4 + (lane >> 3);
-}
-
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kLog2_255 = 7.994353436858858f;
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// Stage one batch: thread tr loads Gaussian `idx` (if in range) into slot tr.
-// Shared-memory record per Gaussian (exponent pre-scaled to base 2 so that the per-pair
-// evaluation is 5 FMA-pipe ops + one MUFU.EX2):
-//   s_geom  = (x, y, L = log2(opacity), flatten id)
-//   s_conic = (A', B', C', 1/opacity)  with  A' = -a/2 log2e, B' = -b log2e, C' = -c/2 log2e
-//   => opacity * exp(-sigma) = exp2(L + A' dx^2 + B' dx dy + C' dy^2)
-//   s_mask  = bit w set iff the Gaussian can reach alpha >= 1/255 on some pixel of warp w's 8x4
-//             block: the ellipse {sigma <= ln(255 o)} has the bounding box
-//             |dx| <= sqrt(2 tau cov_xx), |dy| <= sqrt(2 tau cov_yy); the test is conservative
-//             (slack for rounding), so skipping never changes a result.
-template <int D, bool kStageColors = true>
-__device__ __forceinline__ void stage_gaussian(const BlendArgs &a, int c, int64_t idx, bool in_range, int tr,
-                                               int tile_x0, int tile_y0, float4 *s_geom, float4 *s_conic,
-                                               float *s_col, uint32_t *s_mask) {
-    constexpr int DS = BlendCfg<D>::DS;
-    if (!in_range) {
-        s_mask[tr] = 0u;
-        return;
-    }
-    int32_t g = __ldg(a.flatten_ids + idx);
-    int32_t gl = g - c * a.G;
-    float2 xy = __ldg(reinterpret_cast<const float2 *>(a.means2d) + g);
-    float opac = __ldg(a.opacities + gl);
-    const float *cp = a.conics + 3LL * g;
-    const float ca = __ldg(cp), cb = __ldg(cp + 1), cc = __ldg(cp + 2);
-    const float L = __log2f(opac);
-    s_geom[tr] = make_float4(xy.x, xy.y, L, __int_as_float(g));
-    s_conic[tr] = make_float4(-0.5f * kLog2e * ca, -kLog2e * cb, -0.5f * kLog2e * cc, 1.0f / opac);
-    // per-warp reach mask
-    uint32_t mask = 0u;
-    const float tau = (L + kLog2_255) * kLn2;  // ln(255 * opacity)
-    const float det = ca * cc - cb * cb;
-    if (!(det > 0.f) || !(ca > 0.f) || !(cc > 0.f)) {
-        mask = 0xffu;  // degenerate conic: no culling
-    } else if (tau >= 0.f) {
-        const float k = 2.0f * tau / det;
-        const float ex = sqrtf(k * cc) * 1.0001f + 1e-3f;
-        const float ey = sqrtf(k * ca) * 1.0001f + 1e-3f;
-        const float rx = xy.x - (float)tile_x0, ry = xy.y - (float)tile_y0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const float x0 = (float)((w & 1) * 8) + 0.5f, y0 = (float)((w >> 1) * 4) + 0.5f;
-            const bool hit = (rx >= x0 - ex) && (rx <= x0 + 7.0f + ex) && (ry >= y0 - ey) && (ry <= y0 + 3.0f + ey);
-            mask |= hit ? (1u << w) : 0u;
-        }
-    }
-    s_mask[tr] = mask;
-    if constexpr (!kStageColors) return;
-    const float *col = a.colors + c * a.colors_cs + (int64_t)gl * a.D0;
-    float *dst = s_col + tr * DS;
-    const int d0 = a.depths ? D - 1 : D;
-    if ((d0 & 3) == 0) {
-#pragma unroll
-        for (int k = 0; k < D / 4; ++k) {
-            if (4 * k < d0) {
-                float4 v = __ldg(reinterpret_cast<const float4 *>(col) + k);
-                *reinterpret_cast<float4 *>(dst + 4 * k) = v;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < D; ++k)
-            if (k < d0) dst[k] = __ldg(col + k);
-    }
-    if (a.depths) dst[D - 1] = __ldg(a.depths + g);
-#pragma unroll
-    for (int k = D; k < DS; ++k) dst[k] = 0.f;  // pad lanes feed the packed fp32x2 path: keep them finite
-}
 
 // ----------------------------------------------------------------------------- forward
 template <int D>
@@ -670,6 +562,8 @@ constexpr int kSfStride = 36;  // 32 pixels + 4: conflict-free for all fragment 
 // group of 16 Gaussians pays ~350-480 instructions of split / fragment / atomic overhead, and issue slots are
 // only 61 % busy (barrier + short-scoreboard stalls).  Off by default; D4_BWD_TC=1 enables it for A/B runs.
 constexpr int kDefaultTcBwd = 0;
+constexpr int kDefaultBwdMode = 1;  // 1 = grouped backward (blend_bwd_gp.cu), 0 = shuffle kernel of this file
+constexpr int kDefaultGpCfg = 0;
 
 template <int D>
 struct TcCfg {
@@ -984,11 +878,26 @@ static bool use_tc_bwd() {
     }
     return v != 0;
 }
+// D4_BWD selects the backward formulation: "gp" = grouped (blend_bwd_gp.cu), "shfl" = warp-butterfly kernel below.
+// Read on every call so that one process can A/B the two (tests, scripts/ab_blend_bwd.py).
+static int bwd_mode() {
+    const char *e = getenv("D4_BWD");
+    if (!e) return kDefaultBwdMode;
+    return (e[0] == 's') ? 0 : 1;
+}
+static int bwd_gp_cfg() {
+    const char *e = getenv("D4_BWD_GP_CFG");
+    return e ? atoi(e) : kDefaultGpCfg;
+}
 
 template <int D>
 static int launch_bwd(const BlendArgs &a, const float *ra, const int32_t *li, const float *ad, const float *vrc,
                       const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd, cudaStream_t st) {
     int grid = a.C * a.tile_w * a.tile_h;
+    if (bwd_mode() == 1 && !use_tc_bwd()) {
+        const int rc = launch_blend_bwd_gp(D, bwd_gp_cfg(), a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd, st);
+        if (rc >= 0) return rc;
+    }
     if constexpr (D == 16 || D == 17) {
         if (use_tc_bwd()) {
             constexpr size_t smem_tc = TcCfg<D>::smem_bytes();
@@ -1013,8 +922,6 @@ static int launch_bwd(const BlendArgs &a, const float *ra, const int32_t *li, co
     blend_bwd_kernel<D><<<grid, kBlendThreads, smem, st>>>(a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd);
     return 0;
 }
-
-#define D4_FOR_EACH_D(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(16) X(17) X(32) X(33)
 
 }  // namespace d4
 
