@@ -20,34 +20,36 @@
 // staging of the next batch) is shared with blend.cu.
 #include <limits.h>
 
+#include <type_traits>
+
 #include "blend_common.cuh"
 
 namespace d4 {
 
-constexpr int kGrp = 16;        // Gaussians parked per warp before one phase-2 sweep
 constexpr int kGrpStride = 33;  // 32 pixels + 1: conflict-free for the phase-1 row writes and the phase-2 reads
 
-template <int D, int B>
+// GR = Gaussians parked per warp before one phase-2 sweep (8 or 16); 32 / GR lanes share one Gaussian
+template <int D, int B, int GR>
 struct GpCfg {
     static constexpr int DS = BlendCfg<D>::DS;
     static constexpr int V = BlendCfg<D>::V;
     static constexpr int VS = V | 1;  // odd accumulator stride
-    static constexpr int NH = (V + 1) / 2;  // values owned by each half-warp after the exchange
     static constexpr size_t smem_bytes() {
         return sizeof(float4) * 2 * B + sizeof(float) * B * (DS + VS) + sizeof(float) * kBlendThreads * DS +
-               sizeof(float) * (kBlendThreads / 32) * 2 * kGrp * kGrpStride;
+               sizeof(float) * (kBlendThreads / 32) * 2 * GR * kGrpStride;
     }
 };
 
-template <int D, int B, int MINB, int U>
+template <int D, int B, int MINB, int U, int GR>
 __global__ void __launch_bounds__(kBlendThreads, MINB)
 blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
                     const float *__restrict__ acc_depth, const float *__restrict__ v_render_colors,
                     const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
                     float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opacities,
                     float *__restrict__ v_depths) {
-    using Cfg = GpCfg<D, B>;
-    constexpr int DS = Cfg::DS, V = Cfg::V, VS = Cfg::VS, NH = Cfg::NH;
+    using Cfg = GpCfg<D, B, GR>;
+    constexpr int DS = Cfg::DS, V = Cfg::V, VS = Cfg::VS;
+    static_assert(GR == 8 || GR == 16, "phase-2 group is 8 or 16 Gaussians");
     constexpr int NW = kBlendThreads / 32;
     static_assert(B % 32 == 0 && B <= kBlendThreads, "batch must be a multiple of the warp size and <= 256");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -56,10 +58,10 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
     float *s_col = reinterpret_cast<float *>(s_conic + B);
     float *s_vout = s_col + B * DS;                 // [256 pixels][DS], pixel index == thread index
     float *s_acc = s_vout + kBlendThreads * DS;     // [B][VS]
-    float *s_tiles = s_acc + B * VS;                // [8 warps][2][kGrp][kGrpStride]
+    float *s_tiles = s_acc + B * VS;                // [8 warps][2][GR][kGrpStride]
     __shared__ int32_t s_max[NW];
     __shared__ uint32_t s_mask[B];
-    __shared__ int32_t s_slot[NW][kGrp];
+    __shared__ int32_t s_slot[NW][GR];
     __shared__ int32_t s_gid[2][B];  // flatten ids of the batch being processed / being flushed
 
     const int n_tiles = a.tile_w * a.tile_h;
@@ -133,18 +135,21 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
     if (range_end <= range_start) return;
     const int num_batches = (int)((range_end - range_start + B - 1) / B);
 
-    float *s_fac = s_tiles + w * 2 * kGrp * kGrpStride;
-    float *s_vs = s_fac + kGrp * kGrpStride;
-    // phase-2 geometry of this lane: Gaussian row g, pixel rows [2*half, 2*half + 2) of the warp's 8x4 block
-    const int pg = lane & (kGrp - 1), half = lane >> 4;
+    float *s_fac = s_tiles + w * 2 * GR * kGrpStride;
+    float *s_vs = s_fac + GR * kGrpStride;
     const float bx0 = (float)(tx * kTile + (w & 1) * 8) + 0.5f;
-    const float by0 = (float)(ty * kTile + (w >> 1) * 4 + 2 * half) + 0.5f;
-    const float *p2_vo = s_vout + (w * 32 + half * 16) * DS;
     int nb = 0;  // Gaussians parked in the warp's tile (warp-uniform)
 
-    // ---- phase 2: lane (pg, half) sweeps 16 pixels for Gaussian row pg
-    auto sweep_group = [&]() {
+    // ---- phase 2: GS Gaussians per sweep; lane (pg, part) sweeps 32 / PARTS = GS pixels for Gaussian row pg,
+    // pixels [part*GS, part*GS + GS) of the warp's 8x4 block (pixel p sits at x = p & 7, y = p >> 3)
+    auto sweep_group = [&](auto gs_tag) {
+        constexpr int GS = decltype(gs_tag)::value;
+        constexpr int PARTS = 32 / GS;
+        constexpr int NHP = (V + PARTS - 1) / PARTS;  // values owned by each part after the exchange
         __syncwarp();
+        const int pg = lane & (GS - 1), part = lane / GS;
+        const float by0 = (float)(ty * kTile + (w >> 1) * 4 + (part * GS) / 8) + 0.5f;
+        const float *p2_vo = s_vout + (w * 32 + part * GS) * DS;
         const bool rowok = pg < nb;
         const int t = rowok ? s_slot[w][pg] : 0;
         const float4 g0 = s_geom[t], cn = s_conic[t];
@@ -153,10 +158,10 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
 #pragma unroll
         for (int k = 0; k < DS / 2; ++k) acc[k] = make_float2(0.f, 0.f);
         float axx = 0.f, axy = 0.f, ayy = 0.f, ax = 0.f, ay = 0.f, a0 = 0.f;
-        const float *fr = s_fac + pg * kGrpStride + half * 16;
-        const float *vr = s_vs + pg * kGrpStride + half * 16;
+        const float *fr = s_fac + pg * kGrpStride + part * GS;
+        const float *vr = s_vs + pg * kGrpStride + part * GS;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < GS; ++q) {
             const float fac = fr[q], vs = vr[q];
             const float2 f2 = make_float2(fac, fac);
 #pragma unroll
@@ -174,9 +179,9 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
             ay += t2;
             a0 += vs;
         }
-        // the D+6 values of this half (all linear in the moments, so the halves simply add)
+        // the D+6 values of this part (all linear in the moments, so the parts simply add)
         //   conic (a, b, c) = (-2A', -B', -2C') / log2e ;  cn.w = 1 / opacity
-        float r[2 * NH];
+        float r[PARTS * NHP];
 #pragma unroll
         for (int k = 0; k < D; ++k) r[k] = (k & 1) ? acc[k >> 1].y : acc[k >> 1].x;
         const float ka = cn.x * (-2.0f / kLog2e), kb = cn.y * (-1.0f / kLog2e), kc = cn.z * (-2.0f / kLog2e);
@@ -186,37 +191,74 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
         r[D + 3] = fmaf(ka, ax, kb * ay);
         r[D + 4] = fmaf(kb, ax, kc * ay);
         r[D + 5] = -cn.w * a0;
-        if constexpr (2 * NH > V) r[V] = 0.f;
-        // transposing exchange between the halves: lane (pg, half) ends up owning values [half*NH, half*NH + NH)
-        float *dst = s_acc + t * VS + half * NH;
 #pragma unroll
-        for (int k = 0; k < NH; ++k) {
-            const float send = half ? r[k] : r[k + NH];
-            const float keep = half ? r[k + NH] : r[k];
-            const float mine = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            if (rowok && mine != 0.f && (half * NH + k < V)) atomicAdd(dst + k, mine);
+        for (int k = V; k < PARTS * NHP; ++k) r[k] = 0.f;
+        // transposing exchange between the parts: lane (pg, part) ends up owning values [part*NHP, part*NHP + NHP)
+        {
+            int n = PARTS * NHP;
+#pragma unroll
+            for (int off = 16; off >= GS; off >>= 1) {
+                n >>= 1;
+                const bool upper = (lane & off) != 0;
+#pragma unroll
+                for (int k = 0; k < n; ++k) {
+                    const float send = upper ? r[k] : r[k + n];
+                    const float keep = upper ? r[k + n] : r[k];
+                    r[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
         }
+        float *dst = s_acc + t * VS + part * NHP;
+#pragma unroll
+        for (int k = 0; k < NHP; ++k)
+            if (rowok && r[k] != 0.f && (part * NHP + k < V)) atomicAdd(dst + k, r[k]);
         __syncwarp();
         nb = 0;
     };
 
-    // flush of one batch's CTA-level sums: one global atomic per non-zero (Gaussian, value); zeroes as it goes
+    // flush of one batch's CTA-level sums: one global atomic per non-zero (Gaussian, value); zeroes as it goes.
+    // Warp w takes slots w, w + 8, ...; lane k < V owns value k, so its destination array / stride are fixed.
     auto flush_acc = [&](int n_slots, const int32_t *gids) {
-        const int d0 = a.depths ? D - 1 : D;
-        for (int e = tid; e < n_slots * V; e += kBlendThreads) {
-            const int t = e / V, k = e - t * V;
-            const float val = s_acc[t * VS + k];
-            if (val == 0.f) continue;
-            s_acc[t * VS + k] = 0.f;
+        static_assert(V <= 64, "flush: at most two values per lane");
+        float *fl_base = nullptr;
+        int fl_stride = 0;
+        bool fl_local = false;  // indexed by the camera-local Gaussian id (colours, opacity) instead of the flat id
+        {
+            const int d0 = a.depths ? D - 1 : D;
+            const int k = lane;
+            if (k < d0) { fl_base = v_colors + c * a.colors_cs + k; fl_stride = a.D0; fl_local = true; }
+            else if (k < D) { fl_base = v_depths; fl_stride = 1; }
+            else if (k < D + 3) { fl_base = v_conics + (k - D); fl_stride = 3; }
+            else if (k < D + 5) { fl_base = v_means2d + (k - D - 3); fl_stride = 2; }
+            else if (k < V) { fl_base = v_opacities; fl_stride = 1; fl_local = true; }
+        }
+        for (int t = w; t < n_slots; t += NW) {
             const int32_t g = gids[t];
-            const int32_t gl = g - c * a.G;
-            float *dst;
-            if (k < d0) dst = v_colors + c * a.colors_cs + (int64_t)gl * a.D0 + k;
-            else if (k < D) dst = v_depths + g;
-            else if (k < D + 3) dst = v_conics + 3LL * g + (k - D);
-            else if (k < D + 5) dst = v_means2d + 2LL * g + (k - D - 3);
-            else dst = v_opacities + gl;
-            atomicAdd(dst, val);
+            if (lane < V) {
+                const float val = s_acc[t * VS + lane];
+                if (val != 0.f) {
+                    s_acc[t * VS + lane] = 0.f;
+                    atomicAdd(fl_base + (int64_t)(fl_local ? g - c * a.G : g) * fl_stride, val);
+                }
+            }
+            if constexpr (V > 32) {  // D = 32 / 33: values 32.. are owned a second time by lanes 0..V-33
+                const int k = 32 + lane;
+                if (k < V) {
+                    const float val = s_acc[t * VS + k];
+                    if (val != 0.f) {
+                        s_acc[t * VS + k] = 0.f;
+                        const int d0 = a.depths ? D - 1 : D;
+                        const int32_t gl = g - c * a.G;
+                        float *dst;
+                        if (k < d0) dst = v_colors + c * a.colors_cs + (int64_t)gl * a.D0 + k;
+                        else if (k < D) dst = v_depths + g;
+                        else if (k < D + 3) dst = v_conics + 3LL * g + (k - D);
+                        else if (k < D + 5) dst = v_means2d + 2LL * g + (k - D - 3);
+                        else dst = v_opacities + gl;
+                        atomicAdd(dst, val);
+                    }
+                }
+            }
         }
     };
     int prev_size = 0;
@@ -258,14 +300,19 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
         // validity, <c_g, v_out> -- is evaluated for all U hits first as straight-line independent code (ILP);
         // the recurrence itself is then one FMUL (T) and one FFMA (S) deep per hit.
         bool more = true;
-        while (more) {
+        for (;;) {
             int tu[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 tu[u] = more ? next_hit() : -1;
                 more = tu[u] >= 0;
             }
-            if (tu[0] < 0) break;
+            const bool have = tu[0] >= 0;
+            if (nb > 0 && (!have || nb > GR - U)) {  // make room for U rows / drain at the batch end
+                if (GR == 16 && nb <= 8) sweep_group(std::integral_constant<int, 8>{});  // short drain: 4 lanes per Gaussian
+                else sweep_group(std::integral_constant<int, GR>{});
+            }
+            if (!have) break;
             float al[U], ar[U], sd[U];
             uint32_t cm = 0u;  // hits with at least one contributing pixel in this warp
 #pragma unroll
@@ -310,32 +357,46 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
                     ++nb;
                 }
             }
-            if (nb > kGrp - U) sweep_group();
         }
-        if (nb > 0) sweep_group();
         __syncthreads();  // barrier C: every warp is done with batch b
     }
     flush_acc(prev_size, s_gid[(num_batches & 1) ^ 1]);
 }
 
-template <int D, int B, int MINB, int U>
+// Largest batch (multiple of 32, <= 256) whose shared memory still lets 3 CTAs share an SM
+// (228 KB per SM, 1 KB reserved per CTA, ~12 B / slot + 0.6 KB of static arrays).
+template <int D, int GR>
+constexpr int batch_for_3_ctas() {
+    int best = 32;
+    constexpr size_t per_slot = sizeof(float4) * 2 + sizeof(float) * (BlendCfg<D>::DS + (BlendCfg<D>::V | 1)) + 12;
+    constexpr size_t fixed = sizeof(float) * kBlendThreads * BlendCfg<D>::DS +
+                             sizeof(float) * (kBlendThreads / 32) * 2 * GR * kGrpStride + 640;
+    constexpr size_t budget = (228 * 1024) / 3 - 1024;
+    for (int b = 32; b <= 256; b += 32)
+        if (fixed + per_slot * b <= budget) best = b;
+    return best;
+}
+
+template <int D, int B, int MINB, int U, int GR>
 static int launch_gp(const BlendArgs &a, const float *ra, const int32_t *li, const float *ad, const float *vrc,
                      const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd, cudaStream_t st) {
-    constexpr size_t smem = GpCfg<D, B>::smem_bytes();
+    constexpr size_t smem = GpCfg<D, B, GR>::smem_bytes();
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(blend_bwd_gp_kernel<D, B, MINB, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(blend_bwd_gp_kernel<D, B, MINB, U, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return 1;
         configured = true;
     }
     const int grid = a.C * a.tile_w * a.tile_h;
-    blend_bwd_gp_kernel<D, B, MINB, U><<<grid, kBlendThreads, smem, st>>>(a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd);
+    blend_bwd_gp_kernel<D, B, MINB, U, GR><<<grid, kBlendThreads, smem, st>>>(a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd);
     return 0;
 }
 
-// cfg 0: 256-Gaussian batches, 2 CTAs / SM, 8 hits per phase-1 trip;  cfg 1: 96-Gaussian batches, 3 CTAs / SM;
-// cfg 2 / 3: as 0 / 1 with 4 hits per trip (D <= 17 only; wider D always runs 128-Gaussian batches)
+// launch configurations <batch, CTAs / SM, hits per phase-1 trip, phase-2 group> (D <= 17; wider D runs one fixed shape).
+// Default: the largest batch that keeps 3 CTAs / SM (96 at D = 17, 256 at D <= 8).
+// MEASURED at c3 (D = 17, B200, profiles/r01d_bwd_gp.md): <96,3,4,16> 7.73 ms (default), <128,3,4,8> 8.31, <64,4,4,8> 8.49,
+// <256,2,4,16> 8.67, <96,3,8,16> 8.80, <64,3,4,8> 8.98, <256,2,8,16> 9.66; the shuffle kernel of blend.cu 8.32 ms.
 int launch_blend_bwd_gp(int D, int cfg, const BlendArgs &a, const float *ra, const int32_t *li, const float *ad,
                         const float *vrc, const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd,
                         cudaStream_t st) {
@@ -344,12 +405,10 @@ int launch_blend_bwd_gp(int D, int cfg, const BlendArgs &a, const float *ra, con
 #define X(n)                                                                           \
     case n:                                                                            \
         if constexpr (n <= 17) {                                                       \
-            if (cfg == 1) return launch_gp<n, 96, 3, 8>(GP_ARGS);                      \
-            if (cfg == 2) return launch_gp<n, 256, 2, 4>(GP_ARGS);                     \
-            if (cfg == 3) return launch_gp<n, 96, 3, 4>(GP_ARGS);                      \
-            return launch_gp<n, 256, 2, 8>(GP_ARGS);                                   \
+            if (cfg == 1) return launch_gp<n, 128, 3, 4, 8>(GP_ARGS);                  \
+            return launch_gp<n, batch_for_3_ctas<n, 16>(), 3, 4, 16>(GP_ARGS);         \
         } else {                                                                       \
-            return launch_gp<n, 128, 1, 8>(GP_ARGS);                                   \
+            return launch_gp<n, 128, 1, 4, 16>(GP_ARGS);                               \
         }
         D4_FOR_EACH_D(X)
 #undef X
