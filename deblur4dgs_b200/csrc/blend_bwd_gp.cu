@@ -5,19 +5,27 @@
 // D+6 per-Gaussian sums over pixels are not.  The shuffle kernel in blend.cu pays ~100 issue slots
 // per (warp, Gaussian) for a 32-lane butterfly over those D+6 values; here the two are separated:
 //
-//   phase 1 (lane = pixel):   walk the warp's hit list back to front; per contributing Gaussian
-//       only the two pair scalars  fac = alpha*T  and  v_sigma = dL/dsigma  are produced and
-//       parked in a per-warp [16 Gaussians x 32 pixels] shared-memory tile (2 STS);
-//   phase 2 (lane = Gaussian): once 16 Gaussians are parked, lane (g, half) sweeps 16 of the 32
-//       pixels for ITS Gaussian and accumulates all D+6 sums privately in registers --
+//   phase 1 (lane = pixel):   walk the warp's hit list back to front, U hits per trip.  Everything
+//       that does not depend on the running (T, S) -- exponent, validity vote, <c_g, v_out> -- is
+//       straight-line independent code for the U hits (ILP); the recurrence is then one FMUL (T) and
+//       one FFMA (S) deep per hit.  Per contributing Gaussian only the two pair scalars
+//       fac = alpha*T and v_sigma = dL/dsigma are produced and parked in a per-warp
+//       [GR Gaussians x 32 pixels] shared-memory tile (2 STS) together with a copy of the Gaussian's
+//       geometry record, so a parked row is self-contained and survives the staging of later batches;
+//   phase 2 (lane = Gaussian): once the tile cannot take another trip, lane (g, part) sweeps
+//       32 / PARTS pixels for ITS Gaussian and accumulates all D+6 sums privately in registers --
 //         v_colors[g]  = sum_p fac[g][p] * v_out[p][:]          (packed FFMA2, v_out broadcast from smem)
 //         conic / xy / opacity sums = second moments of v_sigma[g][p] about the Gaussian centre
-//       -- then one 16-lane exchange joins the two halves and the totals go to the per-CTA
-//       accumulator.  No per-Gaussian warp reduction at all: ~35 issue slots per Gaussian.
+//       -- then one exchange joins the parts and each lane issues its share of the D+6 global
+//       reductions (RED.ADD.F32): one per (warp, Gaussian, value).  No per-Gaussian warp reduction,
+//       no CTA-level accumulator, no flush.
 //
-// Everything else (one CTA per (camera, tile), 8x4 pixel block per warp, reach masks, base-2
-// exponent, CTA-level accumulator flushed once per (tile, Gaussian), overlap of the flush with the
-// staging of the next batch) is shared with blend.cu.
+// Staging of the tile's Gaussians (geometry pre-scaled to base 2, colours, per-warp reach masks) is
+// shared with blend.cu; with NBUF = 2 it is double-buffered: batch b+1 is staged by a rotating set of
+// warps while the others already work on batch b, and there is ONE barrier per batch.
+//
+// MEASURED at c3 (D = 17, 9 x 1.49 M intersections, B200; profiles/r01d_*): shuffle kernel 8.32 ms
+// (7.7e9 warp instructions, issue slots 80 % busy); this kernel: see launch_blend_bwd_gp below.
 #include <limits.h>
 
 #include <type_traits>
@@ -26,43 +34,54 @@
 
 namespace d4 {
 
-constexpr int kGrpStride = 33;  // 32 pixels + 1: conflict-free for the phase-1 row writes and the phase-2 reads
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
-// GR = Gaussians parked per warp before one phase-2 sweep (8 or 16); 32 / GR lanes share one Gaussian
-template <int D, int B, int GR>
+// (fac, v_sigma) park tile row stride: 32 pixels + 1, conflict-free for the phase-1 row writes and the phase-2
+// reads.  (An XOR swizzle without the pad column frees 1 KB but costs a LOP3 per sweep step: measured slower.)
+constexpr int kGrpStride = 33;
+
+// B = Gaussians per staged batch, NBUF = staging buffers, GR = rows of the per-warp park tile (8 or 16)
+template <int D, int B, int NBUF, int GR>
 struct GpCfg {
     static constexpr int DS = BlendCfg<D>::DS;
     static constexpr int V = BlendCfg<D>::V;
-    static constexpr int VS = V | 1;  // odd accumulator stride
+    static constexpr int NW = kBlendThreads / 32;
     static constexpr size_t smem_bytes() {
-        return sizeof(float4) * 2 * B + sizeof(float) * B * (DS + VS) + sizeof(float) * kBlendThreads * DS +
-               sizeof(float) * (kBlendThreads / 32) * 2 * GR * kGrpStride;
+        return NBUF * (sizeof(float4) * 2 * B + sizeof(float) * B * DS + sizeof(uint32_t) * B)  // staged batches
+               + sizeof(float) * kBlendThreads * DS                                             // v_out of the tile
+               + sizeof(float) * NW * 2 * GR * kGrpStride                                       // (fac, v_sigma) tiles
+               + sizeof(float4) * NW * GR * 2                                                   // parked geometry
+               + NW * B;                                                                        // per-warp hit lists
     }
 };
 
-template <int D, int B, int MINB, int U, int GR>
+template <int D, int B, int NBUF, int MINB, int U, int GR, bool HL>
 __global__ void __launch_bounds__(kBlendThreads, MINB)
 blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
                     const float *__restrict__ acc_depth, const float *__restrict__ v_render_colors,
                     const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
                     float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opacities,
                     float *__restrict__ v_depths) {
-    using Cfg = GpCfg<D, B, GR>;
-    constexpr int DS = Cfg::DS, V = Cfg::V, VS = Cfg::VS;
-    static_assert(GR == 8 || GR == 16, "phase-2 group is 8 or 16 Gaussians");
-    constexpr int NW = kBlendThreads / 32;
+    using Cfg = GpCfg<D, B, NBUF, GR>;
+    constexpr int DS = Cfg::DS, V = Cfg::V, NW = Cfg::NW;
     static_assert(B % 32 == 0 && B <= kBlendThreads, "batch must be a multiple of the warp size and <= 256");
+    static_assert(GR == 8 || GR == 16, "park tile holds 8 or 16 Gaussians");
+    static_assert(NBUF == 1 || NBUF == 2, "single- or double-buffered staging");
+    static_assert(U == 4 && U <= GR / 2, "a trip is four hits (one packed word of the hit list)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *s_geom = reinterpret_cast<float4 *>(smem_raw);
-    float4 *s_conic = s_geom + B;
-    float *s_col = reinterpret_cast<float *>(s_conic + B);
-    float *s_vout = s_col + B * DS;                 // [256 pixels][DS], pixel index == thread index
-    float *s_acc = s_vout + kBlendThreads * DS;     // [B][VS]
-    float *s_tiles = s_acc + B * VS;                // [8 warps][2][GR][kGrpStride]
+    float4 *s_geom_all = reinterpret_cast<float4 *>(smem_raw);              // [NBUF][B]
+    float4 *s_conic_all = s_geom_all + NBUF * B;                            // [NBUF][B]
+    float4 *s_rows_all = s_conic_all + NBUF * B;                            // [NW][GR][2]  parked (geom, conic)
+    float *s_col_all = reinterpret_cast<float *>(s_rows_all + NW * GR * 2);  // [NBUF][B][DS]
+    float *s_vout = s_col_all + NBUF * B * DS;                              // [256 pixels][DS], pixel == thread
+    float *s_tiles = s_vout + kBlendThreads * DS;                           // [NW][2][GR][kGrpStride]
+    uint32_t *s_mask_all = reinterpret_cast<uint32_t *>(s_tiles + NW * 2 * GR * kGrpStride);  // [NBUF][B]
+    uint8_t *s_hits_all = reinterpret_cast<uint8_t *>(s_mask_all + NBUF * B);                 // [NW][B]
     __shared__ int32_t s_max[NW];
-    __shared__ uint32_t s_mask[B];
-    __shared__ int32_t s_slot[NW][GR];
-    __shared__ int32_t s_gid[2][B];  // flatten ids of the batch being processed / being flushed
 
     const int n_tiles = a.tile_w * a.tile_h;
     const int ct = blockIdx.x;
@@ -126,7 +145,6 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
     // nothing behind the last contributing Gaussian of any pixel of the CTA matters
     const int32_t warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
     if (lane == 0) s_max[w] = warp_bin_final;
-    for (int e = tid; e < B * VS; e += kBlendThreads) s_acc[e] = 0.f;
     __syncthreads();
     int32_t block_bin_final = s_max[0];
 #pragma unroll
@@ -137,6 +155,7 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
 
     float *s_fac = s_tiles + w * 2 * GR * kGrpStride;
     float *s_vs = s_fac + GR * kGrpStride;
+    float4 *s_rows = s_rows_all + w * GR * 2;
     const float bx0 = (float)(tx * kTile + (w & 1) * 8) + 0.5f;
     int nb = 0;  // Gaussians parked in the warp's tile (warp-uniform)
 
@@ -150,9 +169,8 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
         const int pg = lane & (GS - 1), part = lane / GS;
         const float by0 = (float)(ty * kTile + (w >> 1) * 4 + (part * GS) / 8) + 0.5f;
         const float *p2_vo = s_vout + (w * 32 + part * GS) * DS;
-        const bool rowok = pg < nb;
-        const int t = rowok ? s_slot[w][pg] : 0;
-        const float4 g0 = s_geom[t], cn = s_conic[t];
+        const bool rowok = pg < nb;  // rows >= nb hold stale data: computed on, never stored
+        const float4 g0 = s_rows[2 * pg], cn = s_rows[2 * pg + 1];
         const float Xl = g0.x - bx0, Yl = g0.y - by0;
         float2 acc[DS / 2];
 #pragma unroll
@@ -208,111 +226,103 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
                 }
             }
         }
-        float *dst = s_acc + t * VS + part * NHP;
+        // one global reduction per (warp, Gaussian, value)
+        const int d0 = a.depths ? D - 1 : D;
+        const int32_t g = __float_as_int(g0.w);
+        const int32_t gl = g - c * a.G;
 #pragma unroll
-        for (int k = 0; k < NHP; ++k)
-            if (rowok && r[k] != 0.f && (part * NHP + k < V)) atomicAdd(dst + k, r[k]);
+        for (int k = 0; k < NHP; ++k) {
+            const int idx = part * NHP + k;
+            float *dst;
+            if (idx < d0) dst = v_colors + c * a.colors_cs + (int64_t)gl * a.D0 + idx;
+            else if (idx < D) dst = v_depths + g;
+            else if (idx < D + 3) dst = v_conics + 3LL * g + (idx - D);
+            else if (idx < D + 5) dst = v_means2d + 2LL * g + (idx - D - 3);
+            else dst = v_opacities + gl;
+            if (rowok && r[k] != 0.f && idx < V) atomicAdd(dst, r[k]);
+        }
         __syncwarp();
         nb = 0;
     };
 
-    // flush of one batch's CTA-level sums: one global atomic per non-zero (Gaussian, value); zeroes as it goes.
-    // Warp w takes slots w, w + 8, ...; lane k < V owns value k, so its destination array / stride are fixed.
-    auto flush_acc = [&](int n_slots, const int32_t *gids) {
-        static_assert(V <= 64, "flush: at most two values per lane");
-        float *fl_base = nullptr;
-        int fl_stride = 0;
-        bool fl_local = false;  // indexed by the camera-local Gaussian id (colours, opacity) instead of the flat id
-        {
-            const int d0 = a.depths ? D - 1 : D;
-            const int k = lane;
-            if (k < d0) { fl_base = v_colors + c * a.colors_cs + k; fl_stride = a.D0; fl_local = true; }
-            else if (k < D) { fl_base = v_depths; fl_stride = 1; }
-            else if (k < D + 3) { fl_base = v_conics + (k - D); fl_stride = 3; }
-            else if (k < D + 5) { fl_base = v_means2d + (k - D - 3); fl_stride = 2; }
-            else if (k < V) { fl_base = v_opacities; fl_stride = 1; fl_local = true; }
-        }
-        for (int t = w; t < n_slots; t += NW) {
-            const int32_t g = gids[t];
-            if (lane < V) {
-                const float val = s_acc[t * VS + lane];
-                if (val != 0.f) {
-                    s_acc[t * VS + lane] = 0.f;
-                    atomicAdd(fl_base + (int64_t)(fl_local ? g - c * a.G : g) * fl_stride, val);
-                }
-            }
-            if constexpr (V > 32) {  // D = 32 / 33: values 32.. are owned a second time by lanes 0..V-33
-                const int k = 32 + lane;
-                if (k < V) {
-                    const float val = s_acc[t * VS + k];
-                    if (val != 0.f) {
-                        s_acc[t * VS + k] = 0.f;
-                        const int d0 = a.depths ? D - 1 : D;
-                        const int32_t gl = g - c * a.G;
-                        float *dst;
-                        if (k < d0) dst = v_colors + c * a.colors_cs + (int64_t)gl * a.D0 + k;
-                        else if (k < D) dst = v_depths + g;
-                        else if (k < D + 3) dst = v_conics + 3LL * g + (k - D);
-                        else if (k < D + 5) dst = v_means2d + 2LL * g + (k - D - 3);
-                        else dst = v_opacities + gl;
-                        atomicAdd(dst, val);
-                    }
-                }
-            }
+    // staging of batch nbt into buffer buf; with double buffering the B/32 staging warps rotate with the batch
+    // index so that no warp carries the extra work every time
+    auto stage_batch = [&](int nbt, int buf) {
+        constexpr int SW = B / 32;
+        const int rel = NBUF == 2 ? ((w - nbt * SW) & (NW - 1)) : w;
+        if (rel < SW) {
+            const int tr = rel * 32 + lane;
+            const int64_t bend = range_end - 1 - (int64_t)B * nbt;  // slot 0 = furthest back
+            stage_gaussian<D>(a, c, bend - tr, bend - tr >= range_start, tr, tx * kTile, ty * kTile, s_geom_all + buf * B,
+                              s_conic_all + buf * B, s_col_all + buf * B * DS, s_mask_all + buf * B);
         }
     };
-    int prev_size = 0;
+
+    stage_batch(0, 0);
+    __syncthreads();
 
     for (int b = 0; b < num_batches; ++b) {
-        // (barrier C of the previous iteration has passed: every warp is done with batch b-1)
-        const int64_t batch_end = range_end - 1 - (int64_t)B * b;  // slot 0 = furthest back
+        const int buf = NBUF == 2 ? (b & 1) : 0;
+        if (NBUF == 2 && b + 1 < num_batches) stage_batch(b + 1, buf ^ 1);  // overlaps this batch's work
+        const float4 *s_geom = s_geom_all + buf * B;
+        const float4 *s_conic = s_conic_all + buf * B;
+        const float *s_col = s_col_all + buf * B * DS;
+        const uint32_t *s_mask = s_mask_all + buf * B;
+        const int64_t batch_end = range_end - 1 - (int64_t)B * b;
         const int batch_size = (int)min((int64_t)B, batch_end + 1 - range_start);
-        if (tid < B) {
-            const bool in_range = batch_end - tid >= range_start;
-            stage_gaussian<D>(a, c, batch_end - tid, in_range, tid, tx * kTile, ty * kTile, s_geom, s_conic, s_col,
-                              s_mask);
-            s_gid[b & 1][tid] = in_range ? __ldg(a.flatten_ids + (batch_end - tid)) : 0;
-        }
-        flush_acc(prev_size, s_gid[(b & 1) ^ 1]);  // overlaps the staging loads of this batch
-        prev_size = batch_size;
-        __syncthreads();  // barrier B: staging visible, accumulators clean
 
         // slot t holds intersection batch_end - t; this pixel takes part from slot t_px on, the warp from t0 on
         const int t_px = (int)min((int64_t)INT_MAX, batch_end - (int64_t)bin_final);
         const int t0 = (int)max((int64_t)0, batch_end - (int64_t)warp_bin_final);
 
-        // warp-uniform iterator over this warp's hit list (slots whose reach mask has bit w set)
+        // ---- hit list of this warp in the batch: slots whose reach mask has bit w set, from the warp's last
+        // contributor (t0) on.  HL: compacted up front to one byte per hit, a trip then fetches its four slots
+        // with one LDS (fewer instructions; pays off when registers are not the limit, D <= 9).  Otherwise a
+        // warp-uniform bit iterator walks the masks on the fly.
+        uint8_t *s_hits = s_hits_all + w * B;
+        int n_hits = 0;
         int chunk = (t0 >> 5) - 1;
         uint32_t bits = 0u;
+        bool more = true;
+        if constexpr (HL) {
+            for (int ch = t0 >> 5; ch * 32 < batch_size; ++ch) {
+                const int t = ch * 32 + lane;
+                const bool mine = ((s_mask[t] >> w) & 1u) != 0u && t >= t0;
+                const uint32_t bb = __ballot_sync(0xffffffffu, mine);
+                if (mine) s_hits[n_hits + __popc(bb & ((1u << lane) - 1u))] = (uint8_t)t;
+                n_hits += __popc(bb);
+            }
+            __syncwarp();
+        }
         auto next_hit = [&]() -> int {
             while (bits == 0u) {
                 ++chunk;
                 if (chunk * 32 >= batch_size) return -1;
                 bits = __ballot_sync(0xffffffffu, (s_mask[chunk * 32 + lane] >> w) & 1u);
-                if (chunk == (t0 >> 5)) bits &= ~((1u << (t0 & 31)) - 1u);  // slots behind the warp's last contributor
+                if (chunk == (t0 >> 5)) bits &= ~((1u << (t0 & 31)) - 1u);
             }
             const int t = chunk * 32 + __ffs(bits) - 1;
             bits &= bits - 1;
             return t;
         };
 
-        // ---- phase 1, U hits per trip.  Everything that does not depend on the running (T, S) -- exponent,
-        // validity, <c_g, v_out> -- is evaluated for all U hits first as straight-line independent code (ILP);
-        // the recurrence itself is then one FMUL (T) and one FFMA (S) deep per hit.
-        bool more = true;
-        for (;;) {
+        // ---- phase 1, U = 4 hits per trip
+        for (int h = 0;; h += U) {
             int tu[U];
+            if constexpr (HL) {
+                if (h >= n_hits) break;
+                const uint32_t packed = *reinterpret_cast<const uint32_t *>(s_hits + h);  // bytes past n_hits: masked
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                tu[u] = more ? next_hit() : -1;
-                more = tu[u] >= 0;
+                for (int u = 0; u < U; ++u) tu[u] = h + u < n_hits ? (int)((packed >> (8 * u)) & 0xffu) : -1;
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    tu[u] = more ? next_hit() : -1;
+                    more = tu[u] >= 0;
+                }
+                if (tu[0] < 0) break;
             }
-            const bool have = tu[0] >= 0;
-            if (nb > 0 && (!have || nb > GR - U)) {  // make room for U rows / drain at the batch end
-                if (GR == 16 && nb <= 8) sweep_group(std::integral_constant<int, 8>{});  // short drain: 4 lanes per Gaussian
-                else sweep_group(std::integral_constant<int, GR>{});
-            }
-            if (!have) break;
+            if (nb > GR - U) sweep_group(std::integral_constant<int, GR>{});  // make room for U rows
             float al[U], ar[U], sd[U];
             uint32_t cm = 0u;  // hits with at least one contributing pixel in this warp
 #pragma unroll
@@ -344,71 +354,87 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 // alpha == 0 (pixel not taking part): ra = 1, T and S unchanged, fac = v_sigma = 0
-                const float ra = __fdividef(1.0f, 1.0f - al[u]);  // alpha <= 0.999: MUFU.RCP is within 1 ulp here
+                const float ra = rcp_approx(1.0f - al[u]);  // 1 - alpha in [0.001, 1]: MUFU.RCP is within 1 ulp here
                 T *= ra;
                 const float fac = al[u] * T;
                 const float v_alpha = sd[u] * T - (S - tail) * ra;
                 S = fmaf(sd[u], fac, S);
                 const float vs = ar[u] != 0.f ? -ar[u] * v_alpha : 0.f;
-                if ((cm >> u) & 1u) {  // warp-uniform: park the row
+                if ((cm >> u) & 1u) {  // warp-uniform: park the row with a copy of its geometry record
                     s_fac[nb * kGrpStride + lane] = fac;
                     s_vs[nb * kGrpStride + lane] = vs;
-                    if (lane == 0) s_slot[w][nb] = tu[u];
+                    if (lane < 8) {
+                        const float *src = reinterpret_cast<const float *>(lane < 4 ? s_geom + tu[u] : s_conic + tu[u]);
+                        reinterpret_cast<float *>(s_rows + 2 * nb)[lane] = src[lane & 3];
+                    }
                     ++nb;
                 }
             }
         }
-        __syncthreads();  // barrier C: every warp is done with batch b
+        __syncthreads();  // every warp is done with this batch's buffer (and the next batch is staged)
+        if (NBUF == 1 && b + 1 < num_batches) {
+            stage_batch(b + 1, 0);
+            __syncthreads();
+        }
     }
-    flush_acc(prev_size, s_gid[(num_batches & 1) ^ 1]);
+    // drain what is still parked
+    if (nb > 0) {
+        if (GR == 16 && nb <= 8) sweep_group(std::integral_constant<int, 8>{});  // 4 lanes per Gaussian
+        else sweep_group(std::integral_constant<int, GR>{});
+    }
 }
 
-// Largest batch (multiple of 32, <= 256) whose shared memory still lets 3 CTAs share an SM
-// (228 KB per SM, 1 KB reserved per CTA, ~12 B / slot + 0.6 KB of static arrays).
-template <int D, int GR>
-constexpr int batch_for_3_ctas() {
-    int best = 32;
-    constexpr size_t per_slot = sizeof(float4) * 2 + sizeof(float) * (BlendCfg<D>::DS + (BlendCfg<D>::V | 1)) + 12;
-    constexpr size_t fixed = sizeof(float) * kBlendThreads * BlendCfg<D>::DS +
-                             sizeof(float) * (kBlendThreads / 32) * 2 * GR * kGrpStride + 640;
-    constexpr size_t budget = (228 * 1024) / 3 - 1024;
-    for (int b = 32; b <= 256; b += 32)
-        if (fixed + per_slot * b <= budget) best = b;
-    return best;
-}
-
-template <int D, int B, int MINB, int U, int GR>
+template <int D, int B, int NBUF, int MINB, int U, int GR, bool HL = (D <= 9)>
 static int launch_gp(const BlendArgs &a, const float *ra, const int32_t *li, const float *ad, const float *vrc,
                      const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd, cudaStream_t st) {
-    constexpr size_t smem = GpCfg<D, B, GR>::smem_bytes();
+    constexpr size_t smem = GpCfg<D, B, NBUF, GR>::smem_bytes();
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(blend_bwd_gp_kernel<D, B, MINB, U, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(blend_bwd_gp_kernel<D, B, NBUF, MINB, U, GR, HL>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return 1;
         configured = true;
     }
     const int grid = a.C * a.tile_w * a.tile_h;
-    blend_bwd_gp_kernel<D, B, MINB, U, GR><<<grid, kBlendThreads, smem, st>>>(a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd);
+    blend_bwd_gp_kernel<D, B, NBUF, MINB, U, GR, HL><<<grid, kBlendThreads, smem, st>>>(a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd);
     return 0;
 }
 
-// launch configurations <batch, CTAs / SM, hits per phase-1 trip, phase-2 group> (D <= 17; wider D runs one fixed shape).
-// Default: the largest batch that keeps 3 CTAs / SM (96 at D = 17, 256 at D <= 8).
-// MEASURED at c3 (D = 17, B200, profiles/r01d_bwd_gp.md): <96,3,4,16> 7.73 ms (default), <128,3,4,8> 8.31, <64,4,4,8> 8.49,
-// <256,2,4,16> 8.67, <96,3,8,16> 8.80, <64,3,4,8> 8.98, <256,2,8,16> 9.66; the shuffle kernel of blend.cu 8.32 ms.
+// Largest batch (multiple of 32, <= 256) whose shared memory still lets NCTA CTAs share an SM
+// (228 KB per SM, 1 KB reserved per CTA, small static arrays).
+template <int D, int NBUF, int GR, int NCTA>
+constexpr int batch_for() {
+    constexpr size_t budget = (228 * 1024) / NCTA - 1024 - 64;
+    int best = 32;
+    for (int b = 32; b <= 256; b += 32) {
+        const size_t per_slot = NBUF * (sizeof(float4) * 2 + sizeof(float) * BlendCfg<D>::DS + sizeof(uint32_t)) + kBlendThreads / 32;
+        const size_t fixed = sizeof(float) * kBlendThreads * BlendCfg<D>::DS +
+                             sizeof(float) * (kBlendThreads / 32) * 2 * GR * kGrpStride +
+                             sizeof(float4) * (kBlendThreads / 32) * GR * 2;
+        if (fixed + per_slot * b <= budget) best = b;
+    }
+    return best;
+}
+
+// launch configurations (cfg = D4_BWD_GP_CFG): 0 = single-buffered staging, largest batch for 3 CTAs / SM (default);
+// 1 = double-buffered staging, one barrier per batch; 2 = as 1 with an 8-row park tile and 4 CTAs / SM.
+// MEASURED at c3 (B200, N = 9 x 1.49 M intersections; blend_bwd ms): D = 17: cfg 0 7.04, cfg 1 7.53, cfg 2 8.31,
+// 8-row tile with 256-slot batches 7.70, compacted hit list 7.35; shuffle kernel (blend.cu) 8.32.
+// D = 5: cfg 0 4.22 (compacted hit list; 4.54 without), cfg 1 5.08, cfg 2 5.24; shuffle kernel 6.10.
+// Larger batches matter more than one barrier less (cfg 1 halves the batch), 16-row sweeps more than occupancy.
 int launch_blend_bwd_gp(int D, int cfg, const BlendArgs &a, const float *ra, const int32_t *li, const float *ad,
                         const float *vrc, const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd,
                         cudaStream_t st) {
 #define GP_ARGS a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd, st
     switch (D) {
-#define X(n)                                                                           \
-    case n:                                                                            \
-        if constexpr (n <= 17) {                                                       \
-            if (cfg == 1) return launch_gp<n, 128, 3, 4, 8>(GP_ARGS);                  \
-            return launch_gp<n, batch_for_3_ctas<n, 16>(), 3, 4, 16>(GP_ARGS);         \
-        } else {                                                                       \
-            return launch_gp<n, 128, 1, 4, 16>(GP_ARGS);                               \
+#define X(n)                                                                                          \
+    case n:                                                                                           \
+        if constexpr (n <= 17) {                                                                      \
+            if (cfg == 1) return launch_gp<n, batch_for<n, 2, 16, 3>(), 2, 3, 4, 16>(GP_ARGS);        \
+            if (cfg == 2) return launch_gp<n, batch_for<n, 2, 8, 4>(), 2, 4, 4, 8>(GP_ARGS);          \
+            return launch_gp<n, batch_for<n, 1, 16, 3>(), 1, 3, 4, 16>(GP_ARGS);                      \
+        } else {                                                                                      \
+            return launch_gp<n, 128, 1, 1, 4, 16>(GP_ARGS);                                           \
         }
         D4_FOR_EACH_D(X)
 #undef X

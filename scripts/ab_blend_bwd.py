@@ -50,14 +50,21 @@ def main():
                                 p["rots"], p["transls"], sc.times, sc.RTs, scales, opac, colors, sc.w2c, sc.K, W, H,
                                 backgrounds=bg, render_mode="RGB+ED", combine=True, ref_quirk=True)
         torch.autograd.backward([o["img"], o["acc"]], [w_img, w_acc])
-        return {k: p[k].grad for k in names}, int(o["meta"]["isect_ids"].numel())
+        g = {k: p[k].grad for k in names}
+        g["img"], g["acc"] = o["img"].detach(), o["acc"].detach()
+        return g, int(o["meta"]["isect_ids"].numel())
 
     base = None
     for mode in args.modes:
-        kind, _, cfg = mode.partition(":")
-        os.environ["D4_BWD"] = kind
-        if cfg:
-            os.environ["D4_BWD_GP_CFG"] = cfg
+        if "=" in mode:  # generic form: ENV=VAL[,ENV=VAL...]
+            for kv in mode.split(","):
+                k, _, v = kv.partition("=")
+                os.environ[k] = v
+        else:  # shorthand: shfl | gp[:cfg]
+            kind, _, cfg = mode.partition(":")
+            os.environ["D4_BWD"] = kind
+            if cfg:
+                os.environ["D4_BWD_GP_CFG"] = cfg
         for _ in range(2):
             grads, n_isects = step()
         torch.cuda.synchronize()
@@ -72,7 +79,7 @@ def main():
         if base is None:
             base = {k: v.clone() for k, v in grads.items()}
         else:
-            for k in names:
+            for k in base:
                 scale = base[k].abs().max().item() + 1e-30
                 dev_rel[k] = (grads[k] - base[k]).abs().max().item() / scale
         print(json.dumps({"mode": mode, "config": args.config, "D": D0 + 1, "n_isects": n_isects,

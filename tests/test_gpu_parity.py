@@ -31,7 +31,7 @@ from util import golden, golden_files, quat_sign_align, rel_err, scale_err
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 # backward blend formulations under test: grouped (default; both launch configurations) and warp-butterfly
-BWD_MODES = ["gp:0", "gp:1", "shfl"]  # gp:0 is the default
+BWD_MODES = ["gp:0", "gp:1", "gp:2", "shfl"]  # gp:0 is the default
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
 
 
