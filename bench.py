@@ -40,6 +40,20 @@ UNIT = "frames/s"
 D0_SYNTH = 16  # rgb(3) + fg mask(1) + 4x3 track channels; +1 expected depth => D = 17 (scene_model.py:205-296)
 
 
+def measured_traffic(prefix):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/traffic.json, written by scripts/ncu_summary.py); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    for k, v in d.items():
+        if k.startswith(prefix):
+            return v.get("dram_bytes_per_launch"), f"{k} in profiles/traffic.json ({v.get('source')}, grid {v.get('grid')})"
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -362,6 +376,9 @@ def main():
         peak, peak_src = peaks()
         dom = "d4_blend_bwd"
         dom_ms = kernel_ms.get(dom, float("nan"))
+        traffic, traffic_src = measured_traffic(f"blend_bwd_gp_kernel<{Dtot}")
+        if args.config != "c3" or world != 1 or args.checkpoint:
+            traffic, traffic_src = None, None  # the capture is of the c3 single-GPU launch
         dom_bytes = ab["blend_bwd"] * frames_per_step_local
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         step_bytes = sum(ab.values()) * frames_per_step_local
@@ -372,10 +389,11 @@ def main():
             "data": "synthetic (seeded, SURVEY 8d); random-init scene, no dataset/checkpoint",
             "config": workload_config(args, sc),
             "n_isects_per_frame": I_frame,
-            "roofline": {"bound": "hbm", "kernel": "blend_bwd_kernel<17> (d4_blend_bwd)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": f"blend_bwd_gp_kernel<{Dtot}> (d4_blend_bwd)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
-                         "note": "blend is fp32-issue/MUFU/shuffle bound, not HBM bound (DESIGN.md); whole-step "
+                         "note": "blend is fp32-issue / latency bound, not HBM bound (DESIGN.md); whole-step "
                                  "algorithmic-bytes rate is in step_hbm"},
             "step_hbm": {"algorithmic_bytes_per_step": step_bytes,
                          "achieved_gbs": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,

@@ -76,7 +76,31 @@ def full(src, dst):
                 if k in idx:
                     f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
             f.write("\n")
+            _record_traffic(name, r, idx, units, src)
     print(open(dst).read())
+
+
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def _record_traffic(name, r, idx, units, src):
+    """profiles/traffic.json: DRAM bytes (read + write) of one launch per kernel, the figure bench.py reports as
+    roofline.traffic.  Keyed by the kernel name up to its first template argument (e.g. blend_bwd_gp_kernel<17)."""
+    import json
+    import os
+    import re
+    if "dram__bytes_read.sum" not in idx:
+        return
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        tot += float(r[idx[k]].replace(",", "")) * _UNIT.get(units[idx[k]], 1.0)
+    m = re.match(r"(?:void )?(?:d4::)?(\w+)<(?:\(int\))?(\d+)", name)
+    key = f"{m.group(1)}<{m.group(2)}" if m else name
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    d[key] = {"dram_bytes_per_launch": tot, "ms": float(r[idx["gpu__time_duration.sum"]].replace(",", "")) if "gpu__time_duration.sum" in idx else None,
+              "source": os.path.basename(src), "grid": r[idx["launch__grid_size"]] if "launch__grid_size" in idx else None}
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
