@@ -188,9 +188,12 @@ def test_rasterization_c1_config():
     (20000, 500, 277, 4, "RGB+ED", 2, 2.0),    # static pass: D = 5, ragged image edge, 2 cameras
     (5000, 130, 70, 3, "RGB", 1, 6.0),         # fat Gaussians: long per-tile lists, early termination
     (3000, 64, 48, 5, "RGB+D", 1, 2.0),        # D = 6
+    (3000, 96, 64, 32, "RGB+ED", 1, 2.0),      # D = 33: the wide kernels (one 128-slot batch shape)
+    (2000, 80, 48, 11, "RGB+D", 1, 2.0),       # D = 12: zero-padded to the 16-channel build
+    (2000, 80, 48, 40, "RGB+ED", 1, 2.0),      # 40 feature channels: chunked 32 + (8 + depth), as gsplat chunks
 ])
 def test_rasterization_vs_oracle(G, W, H, d0, mode, C, scale_mult):
-    sc = make_scene(G=G, width=W, height=H, K=4, N=1, seed=G + W, scale_mult=scale_mult)
+    sc = make_scene(G=G, width=W, height=H, K=4, N=1, seed=G + W, scale_mult=scale_mult, d_extra=max(12, d0 - 4))
     inp = scene_inputs(sc, d0, C)
     check_raster_against(f"G{G}_{W}x{H}_d{d0}_{mode}_C{C}", inp, W, H, mode, oracle_ref(inp, W, H, mode))
 
