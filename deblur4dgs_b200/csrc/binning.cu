@@ -11,6 +11,8 @@
 //       key its rank among equal digits; CTA-level digit bases come from (2).
 // No decoupled look-back / spin-waiting anywhere: every kernel is a plain
 // bulk-synchronous pass, so a scheduling surprise cannot hang the device.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace d4 {
@@ -272,10 +274,18 @@ __device__ __forceinline__ void tile_rect_dev(float m2x, float m2y, int32_t radi
     y1 = (int)fminf(fmaxf(ceilf(__fadd_rn(ty, tr)), 0.f), fh);
 }
 
+// kLanesPerGauss threads share one Gaussian and stride over its tile rectangle: the tile counts per Gaussian are
+// heavy-tailed (a few large Gaussians cover hundreds of tiles), and the emit loop is a chain of returning atomics
+// (measured at c3: 1 lane 0.327 / 0.355 ms for count / emit, 4 lanes 0.184 / 0.248, 8 lanes the same, 16 lanes
+// 0.268 / 0.314 -- with 4 the count runs at the L2 atomic rate, ~70 G atomics/s)
+constexpr int kLanesPerGauss = 4;
+
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii, int C, int G, int tile_size,
                   int tile_w, int tile_h, int32_t *__restrict__ tile_counts) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t idx = tg / kLanesPerGauss;
+    const int sub = (int)(tg - idx * kLanesPerGauss);
     if (idx >= (int64_t)C * G) return;
     const int32_t r = radii[idx];
     if (r <= 0) return;
@@ -283,8 +293,11 @@ tile_count_kernel(const float *__restrict__ means2d, const int32_t *__restrict__
     int x0, y0, x1, y1;
     tile_rect_dev(m2.x, m2.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
     int32_t *cnt = tile_counts + (idx / G) * (int64_t)tile_w * tile_h;
-    for (int i = y0; i < y1; ++i)
-        for (int j = x0; j < x1; ++j) atomicAdd(cnt + i * tile_w + j, 1);
+    const int wx = x1 - x0, n = wx * (y1 - y0);
+    for (int q = sub; q < n; q += kLanesPerGauss) {
+        const int i = q / wx, j = q - i * wx;
+        atomicAdd(cnt + (y0 + i) * tile_w + x0 + j, 1);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -292,7 +305,9 @@ bucket_emit_kernel(const float *__restrict__ means2d, const int32_t *__restrict_
                    const float *__restrict__ depths, int C, int G, int tile_size, int tile_w, int tile_h,
                    const int32_t *__restrict__ tile_offsets, int32_t *__restrict__ cursors,
                    uint64_t *__restrict__ bucket_keys) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t idx = tg / kLanesPerGauss;
+    const int sub = (int)(tg - idx * kLanesPerGauss);
     if (idx >= (int64_t)C * G) return;
     const int32_t r = radii[idx];
     if (r <= 0) return;
@@ -301,12 +316,13 @@ bucket_emit_kernel(const float *__restrict__ means2d, const int32_t *__restrict_
     tile_rect_dev(m2.x, m2.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
     const int64_t cbase = (idx / G) * (int64_t)tile_w * tile_h;
     const uint64_t key = ((uint64_t)(uint32_t)__float_as_int(depths[idx]) << 32) | (uint32_t)idx;
-    for (int i = y0; i < y1; ++i)
-        for (int j = x0; j < x1; ++j) {
-            const int64_t t = cbase + i * tile_w + j;
-            const int32_t pos = tile_offsets[t] + atomicAdd(cursors + t, 1);
-            bucket_keys[pos] = key;
-        }
+    const int wx = x1 - x0, n = wx * (y1 - y0);
+    for (int q = sub; q < n; q += kLanesPerGauss) {
+        const int i = q / wx, j = q - i * wx;
+        const int64_t t = cbase + (y0 + i) * tile_w + x0 + j;
+        const int32_t pos = tile_offsets[t] + atomicAdd(cursors + t, 1);
+        bucket_keys[pos] = key;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -358,8 +374,8 @@ extern "C" int d4_tile_count(const float *means2d, const int32_t *radii, int C, 
     D4_CHECK_ARG(C >= 1 && G >= 0 && tile_counts, "d4_tile_count: bad arguments");
     if (G == 0) return 0;
     D4_CHECK_ARG(means2d && radii, "d4_tile_count: null pointer");
-    tile_count_kernel<<<cdiv((int64_t)C * G, 256), 256, 0, as_stream(stream)>>>(means2d, radii, C, G, tile_size, tile_w,
-                                                                               tile_h, tile_counts);
+    tile_count_kernel<<<cdiv((int64_t)C * G * kLanesPerGauss, 256), 256, 0, as_stream(stream)>>>(
+        means2d, radii, C, G, tile_size, tile_w, tile_h, tile_counts);
     D4_CHECK_LAUNCH("d4_tile_count");
     return 0;
 }
@@ -370,7 +386,7 @@ extern "C" int d4_bucket_emit(const float *means2d, const int32_t *radii, const 
     D4_CHECK_ARG(C >= 1 && G >= 0 && (int64_t)C * G < (1LL << 32), "d4_bucket_emit: bad sizes");
     if (G == 0) return 0;
     D4_CHECK_ARG(means2d && radii && depths && tile_offsets && cursors && bucket_keys, "d4_bucket_emit: null pointer");
-    bucket_emit_kernel<<<cdiv((int64_t)C * G, 256), 256, 0, as_stream(stream)>>>(
+    bucket_emit_kernel<<<cdiv((int64_t)C * G * kLanesPerGauss, 256), 256, 0, as_stream(stream)>>>(
         means2d, radii, depths, C, G, tile_size, tile_w, tile_h, tile_offsets, cursors, bucket_keys);
     D4_CHECK_LAUNCH("d4_bucket_emit");
     return 0;

@@ -85,6 +85,7 @@ def main():
         print(json.dumps({"mode": mode, "config": args.config, "D": D0 + 1, "n_isects": n_isects,
                           "blend_bwd_ms": ms.get("d4_blend_bwd"), "blend_fwd_ms": ms.get("d4_blend_fwd"),
                           "step_ms_kernels": sum(ms.values()),
+                          "ms": {k.replace("d4_", ""): round(v, 3) for k, v in ms.items()},
                           "finite": all(bool(torch.isfinite(v).all()) for v in grads.values()),
                           "max_rel_dev_vs_first": max(dev_rel.values()) if dev_rel else 0.0,
                           "worst": max(dev_rel, key=dev_rel.get) if dev_rel else None}), flush=True)
