@@ -42,24 +42,26 @@ class _Combine(torch.autograd.Function):
         P = imgs[0].numel() // D
         out_img = torch.empty_like(imgs[0])
         out_alpha = torch.empty_like(alphas[0])
+        # winner maps of the max / min channel: the backward routes from them, the stack is not kept
+        arg_max = torch.empty((P,), dtype=torch.uint8, device=imgs.device) if 0 <= max_ch < D else None
+        arg_min = torch.empty((P,), dtype=torch.uint8, device=imgs.device) if 0 <= min_ch < D else None
         call("d4_combine_fwd", ptr(imgs), ptr(alphas), N, P, D, max_ch, min_ch, int(ref_quirk), ptr(out_img),
-             ptr(out_alpha), stream_ptr())
-        ctx.save_for_backward(imgs if (max_ch >= 0 or min_ch >= 0) else None)
-        ctx.cfg = (N, P, D, max_ch, min_ch, int(ref_quirk), imgs.shape, alphas.shape)
+             ptr(out_alpha), ptr(arg_max), ptr(arg_min), stream_ptr())
+        ctx.save_for_backward(arg_max, arg_min)
+        ctx.cfg = (N, P, D, max_ch, min_ch, imgs.shape, alphas.shape)
         return out_img, out_alpha
 
     @staticmethod
     def backward(ctx, v_img, v_alpha):
-        (imgs,) = ctx.saved_tensors
-        N, P, D, max_ch, min_ch, ref_quirk, ishape, ashape = ctx.cfg
+        arg_max, arg_min = ctx.saved_tensors
+        N, P, D, max_ch, min_ch, ishape, ashape = ctx.cfg
         dev = v_img.device if v_img is not None else v_alpha.device
         v_img = v_img.contiguous() if v_img is not None else torch.zeros(ishape[1:], device=dev)
         v_alpha = v_alpha.contiguous() if v_alpha is not None else torch.zeros(ashape[1:], device=dev)
         v_imgs = torch.empty(ishape, dtype=torch.float32, device=dev)
         v_alphas = torch.empty(ashape, dtype=torch.float32, device=dev)
-        src = imgs if imgs is not None else v_imgs  # unused by the kernel when there is no max/min channel
-        call("d4_combine_bwd", ptr(src), N, P, D, max_ch, min_ch, ref_quirk, ptr(v_img), ptr(v_alpha), ptr(v_imgs),
-             ptr(v_alphas), stream_ptr())
+        call("d4_combine_bwd", ptr(arg_max), ptr(arg_min), N, P, D, max_ch, min_ch, ptr(v_img), ptr(v_alpha),
+             ptr(v_imgs), ptr(v_alphas), stream_ptr())
         return v_imgs, v_alphas, None, None, None
 
 

@@ -199,13 +199,17 @@ int d4_camera_interp_bwd(const float *start6, const float *end6, int N, const fl
  * tensor is overwritten in place by the average BEFORE the max/min are taken
  * (scene_model.py:391-393), so the extrema run over {r_0..r_{N-2}, mean}
  * instead of {r_0..r_{N-1}}.
+ * arg_max / arg_min [P] (uint8, may be NULL when the channel is absent): the forward records per pixel which
+ * sub-exposure won the max / min channel (255 = the mean itself, ref_quirk only); the backward routes from
+ * them instead of re-reading the N images, so the stack need not be kept for backward.
  * Backward: v_imgs [N,P,D], v_alphas [N,P] overwritten (max/min route the
- * gradient to the first arg-extremum, as torch.max/min(dim) do).               */
+ * gradient to the first arg-extremum, as torch.max/min(dim) do).  N < 255.      */
 int d4_combine_fwd(const float *imgs, const float *alphas, int N, int64_t P, int D, int max_ch,
-                   int min_ch, int ref_quirk, float *out_img, float *out_alpha, d4_stream_t stream);
-int d4_combine_bwd(const float *imgs, int N, int64_t P, int D, int max_ch, int min_ch, int ref_quirk,
-                   const float *v_out_img, const float *v_out_alpha, float *v_imgs, float *v_alphas,
-                   d4_stream_t stream);
+                   int min_ch, int ref_quirk, float *out_img, float *out_alpha, uint8_t *arg_max,
+                   uint8_t *arg_min, d4_stream_t stream);
+int d4_combine_bwd(const uint8_t *arg_max, const uint8_t *arg_min, int N, int64_t P, int D, int max_ch,
+                   int min_ch, const float *v_out_img, const float *v_out_alpha, float *v_imgs,
+                   float *v_alphas, d4_stream_t stream);
 
 /* ---- f1 ("next" row): activations + fg|bg concatenation + feature-vector assembly ------------------
  * replaces GaussianParams' activations (params.py:39-43, 70-84: exp / sigmoid / sigmoid), the fg|bg
