@@ -339,21 +339,40 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
     while (n_pad < n) n_pad <<= 1;
     for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[i] = i < n ? bucket_keys[start + i] : ~0ull;
     __syncthreads();
+    // Bitonic network.  Stages with partner distance j <= 32 only exchange within aligned 64-key chunks: chunk q is
+    // owned by warp q % 8 for the whole sort, so those stages need a warp barrier only.  Block barriers remain
+    // around the stages with j >= 64 (6 of the 45 stages at 512 keys).
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    auto cmpx = [&](int lo, int hi, int k) {
+        const uint64_t a = s_keys[lo], b = s_keys[hi];
+        const bool asc = (lo & k) == 0;
+        if ((a > b) == asc) {
+            s_keys[lo] = b;
+            s_keys[hi] = a;
+        }
+    };
     for (int k = 2; k <= n_pad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < (n_pad >> 1); i += blockDim.x) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const int hi = lo | j;
-                const uint64_t a = s_keys[lo], b = s_keys[hi];
-                const bool asc = (lo & k) == 0;
-                if ((a > b) == asc) {
-                    s_keys[lo] = b;
-                    s_keys[hi] = a;
+        int j = k >> 1;
+        if (j >= 64) {
+            __syncthreads();  // the warp-local tails of the previous k are complete
+            for (; j >= 64; j >>= 1) {
+                for (int i = threadIdx.x; i < (n_pad >> 1); i += blockDim.x) {
+                    const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                    cmpx(lo, lo | j, k);
                 }
+                __syncthreads();
             }
-            __syncthreads();
+        }
+        for (int base = w * 64; base < n_pad; base += n_warps * 64) {
+            for (int jj = j; jj > 0; jj >>= 1) {
+                const int lo = base + (((lane & ~(jj - 1)) << 1) | (lane & (jj - 1)));
+                const int hi = lo | jj;
+                if (hi < n_pad) cmpx(lo, hi, k);
+                __syncwarp();
+            }
         }
     }
+    __syncthreads();
     const int64_t cam = seg / n_tiles, tile = seg - cam * n_tiles;
     const int64_t hi_bits = (cam << (32 + tile_n_bits)) | (tile << 32);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
