@@ -371,10 +371,20 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
                 }
             }
         }
-        __syncthreads();  // every warp is done with this batch's buffer (and the next batch is staged)
-        if (NBUF == 1 && b + 1 < num_batches) {
-            stage_batch(b + 1, 0);
-            __syncthreads();
+        if constexpr (NBUF == 1) {
+            // single buffer: this thread's slot of the next batch is fetched into registers BEFORE the barrier --
+            // the loads fly while the warp waits for the slowest warp of the tile -- and published after it
+            StagedRec<D> rec;
+            const bool stager = b + 1 < num_batches && tid < B;
+            const int64_t bend = range_end - 1 - (int64_t)B * (b + 1);
+            stage_load<D>(rec, a, c, bend - tid, stager && bend - tid >= range_start);
+            __syncthreads();  // every warp is done with this batch's buffer
+            if (b + 1 < num_batches) {
+                if (stager) stage_store<D>(rec, tid, tx * kTile, ty * kTile, s_geom_all, s_conic_all, s_col_all, s_mask_all);
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();  // every warp is done with this batch's buffer and the next batch is staged
         }
     }
     // drain what is still parked

@@ -55,6 +55,94 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //             block: the ellipse {sigma <= ln(255 o)} has the bounding box
 //             |dx| <= sqrt(2 tau cov_xx), |dy| <= sqrt(2 tau cov_yy); the test is conservative
 //             (slack for rounding), so skipping never changes a result.
+// Two-step staging (grouped backward): stage_load issues the global loads of a slot into registers, stage_store
+// publishes the record later -- the loads of the next batch fly while the warp waits at the batch barrier.
+template <int D, bool kStageColors = true>
+struct StagedRec {
+    int32_t g;  // flatten id, -1 when the slot is out of range
+    float x, y, op, ca, cb, cc;
+    float col[kStageColors ? BlendCfg<D>::DS : 1];
+};
+
+template <int D, bool kStageColors = true>
+__device__ __forceinline__ void stage_load(StagedRec<D, kStageColors> &r, const BlendArgs &a, int c, int64_t idx,
+                                           bool in_range) {
+    constexpr int DS = BlendCfg<D>::DS;
+    r.g = -1;
+    r.x = r.y = r.op = r.ca = r.cb = r.cc = 0.f;
+    if constexpr (kStageColors) {
+#pragma unroll
+        for (int k = 0; k < DS; ++k) r.col[k] = 0.f;  // pad lanes feed the packed fp32x2 path: keep them finite
+    }
+    if (in_range) {
+        const int32_t g = __ldg(a.flatten_ids + idx);
+        const int32_t gl = g - c * a.G;
+        r.g = g;
+        const float2 xy = __ldg(reinterpret_cast<const float2 *>(a.means2d) + g);
+        r.x = xy.x, r.y = xy.y;
+        r.op = __ldg(a.opacities + gl);
+        const float *cp = a.conics + 3LL * g;
+        r.ca = __ldg(cp), r.cb = __ldg(cp + 1), r.cc = __ldg(cp + 2);
+        if constexpr (kStageColors) {
+            const float *col = a.colors + c * a.colors_cs + (int64_t)gl * a.D0;
+            const int d0 = a.depths ? D - 1 : D;
+            if ((d0 & 3) == 0) {
+#pragma unroll
+                for (int k = 0; k < D / 4; ++k) {
+                    if (4 * k < d0) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(col) + k);
+                        r.col[4 * k] = v.x, r.col[4 * k + 1] = v.y, r.col[4 * k + 2] = v.z, r.col[4 * k + 3] = v.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d0) r.col[k] = __ldg(col + k);
+            }
+            if (a.depths) r.col[D - 1] = __ldg(a.depths + g);
+        }
+    }
+}
+
+template <int D, bool kStageColors = true>
+__device__ __forceinline__ void stage_store(const StagedRec<D, kStageColors> &r, int tr, int tile_x0, int tile_y0,
+                                            float4 *s_geom, float4 *s_conic, float *s_col, uint32_t *s_mask) {
+    constexpr int DS = BlendCfg<D>::DS;
+    if (r.g < 0) {
+        s_mask[tr] = 0u;
+        return;
+    }
+    const float L = __log2f(r.op);
+    s_geom[tr] = make_float4(r.x, r.y, L, __int_as_float(r.g));
+    s_conic[tr] = make_float4(-0.5f * kLog2e * r.ca, -kLog2e * r.cb, -0.5f * kLog2e * r.cc, 1.0f / r.op);
+    // per-warp reach mask
+    uint32_t mask = 0u;
+    const float tau = (L + kLog2_255) * kLn2;  // ln(255 * opacity)
+    const float det = r.ca * r.cc - r.cb * r.cb;
+    if (!(det > 0.f) || !(r.ca > 0.f) || !(r.cc > 0.f)) {
+        mask = 0xffu;  // degenerate conic: no culling
+    } else if (tau >= 0.f) {
+        const float k = 2.0f * tau / det;
+        const float ex = sqrtf(k * r.cc) * 1.0001f + 1e-3f;
+        const float ey = sqrtf(k * r.ca) * 1.0001f + 1e-3f;
+        const float rx = r.x - (float)tile_x0, ry = r.y - (float)tile_y0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float x0 = (float)((w & 1) * 8) + 0.5f, y0 = (float)((w >> 1) * 4) + 0.5f;
+            const bool hit = (rx >= x0 - ex) && (rx <= x0 + 7.0f + ex) && (ry >= y0 - ey) && (ry <= y0 + 3.0f + ey);
+            mask |= hit ? (1u << w) : 0u;
+        }
+    }
+    s_mask[tr] = mask;
+    if constexpr (kStageColors) {
+        float *dst = s_col + tr * DS;
+#pragma unroll
+        for (int k4 = 0; k4 < DS / 4; ++k4)
+            *reinterpret_cast<float4 *>(dst + 4 * k4) = make_float4(r.col[4 * k4], r.col[4 * k4 + 1], r.col[4 * k4 + 2], r.col[4 * k4 + 3]);
+    }
+}
+
+// one-step staging (forward and shuffle backward): global loads go straight to shared memory
 template <int D, bool kStageColors = true>
 __device__ __forceinline__ void stage_gaussian(const BlendArgs &a, int c, int64_t idx, bool in_range, int tr,
                                                int tile_x0, int tile_y0, float4 *s_geom, float4 *s_conic,
