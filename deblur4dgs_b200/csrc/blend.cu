@@ -65,11 +65,14 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
 #pragma unroll
     for (int k = 0; k < D2; ++k) out2[k] = make_float2(0.f, 0.f);
 
+    // this thread's slot of batch b is fetched into registers at the end of batch b-1: the loads fly while the
+    // warp waits at the batch barrier for the slowest warp of the tile
+    StagedRec<D> rec;
+    stage_load<D>(rec, a, c, range_start + tid, num_batches > 0 && range_start + tid < range_end);
     for (int b = 0; b < num_batches; ++b) {
         if (__syncthreads_count(done) >= kBlendThreads) break;
         const int64_t batch_start = range_start + (int64_t)kBatch * b;
-        stage_gaussian<D>(a, c, batch_start + tid, batch_start + tid < range_end, tid, tx * kTile, ty * kTile, s_geom,
-                          s_conic, s_col, s_mask);
+        stage_store<D>(rec, tid, tx * kTile, ty * kTile, s_geom, s_conic, s_col, s_mask);
         __syncthreads();
         const int batch_size = (int)min((int64_t)kBatch, range_end - batch_start);
         bool warp_done = __all_sync(0xffffffffu, done);
@@ -116,6 +119,10 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
                 if (composite(ta, pa, ga.z)) { warp_done = true; break; }
                 if (has_b && composite(tb, pb, gb.z)) { warp_done = true; break; }
             }
+        }
+        {
+            const int64_t next = batch_start + kBatch + tid;
+            stage_load<D>(rec, a, c, next, b + 1 < num_batches && next < range_end);
         }
     }
 
