@@ -46,7 +46,6 @@ PROTOTYPES = {
     "d4_assemble_fwd": (c_int, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P]),
     "d4_assemble_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, P]),
     "d4_densify_stats": (c_int, [P, P, I, I, F, F, F, P, P, P, P]),
-    "d4_publish_i64": (c_int, [P, I, P, P]),
     "d4_combine_fwd": (c_int, [P, P, I, L, I, I, I, I, P, P, P, P, P]),
     "d4_combine_bwd": (c_int, [P, P, I, L, I, I, I, P, P, P, P, P]),
 }

@@ -388,22 +388,6 @@ using namespace d4;
 
 extern "C" int d4_tile_sort_capacity(void) { return kTileSortMax; }
 
-// Device -> host hand-over of a few scalars WITHOUT the copy engine: a kernel stores them into mapped pinned host
-// memory; the host then waits on an event.  A cudaMemcpy-based read-back queues behind whatever bulk download the
-// application has in flight on the same D2H engine (measured: +1.3 ms per step next to an 87 MB result download).
-__global__ void publish_i64_kernel(const int64_t *__restrict__ src, int n, volatile int64_t *dst_host) {
-    const int i = threadIdx.x;
-    if (i < n) dst_host[i] = src[i];
-    __threadfence_system();
-}
-
-extern "C" int d4_publish_i64(const int64_t *src, int n, int64_t *dst_host_mapped, d4_stream_t stream) {
-    D4_CHECK_ARG(src && dst_host_mapped && n >= 1 && n <= 32, "d4_publish_i64: bad arguments");
-    publish_i64_kernel<<<1, 32, 0, as_stream(stream)>>>(src, n, dst_host_mapped);
-    D4_CHECK_LAUNCH("d4_publish_i64");
-    return 0;
-}
-
 extern "C" int d4_tile_count(const float *means2d, const int32_t *radii, int C, int G, int tile_size, int tile_w,
                              int tile_h, int32_t *tile_counts, d4_stream_t stream) {
     D4_CHECK_ARG(C >= 1 && G >= 0 && tile_counts, "d4_tile_count: bad arguments");

@@ -145,7 +145,7 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     cum = torch.empty((C, G), dtype=torch.int32, device=dev)
     total = torch.empty((1,), dtype=torch.int64, device=dev)
     call("d4_exclusive_scan_i32", ptr(tiles_per_gauss), n, ptr(cum), ptr(total), ptr(ws), ws_bytes, st)
-    n_isects = _read_back_i64(total)[0]  # the one device->host sync of the op (as in gsplat)
+    n_isects = int(total.item())  # the one device->host sync of the op (as in gsplat)
     if n_isects >= 2 ** 31:
         raise _cabi.D4Error("more than 2^31 tile intersections")
     isect_ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
@@ -184,18 +184,6 @@ def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height:
     return offsets
 
 
-def _read_back_i64(t: Tensor):
-    """Small int64 device tensor -> python ints, through mapped pinned memory + an event instead of a
-    copy-engine read-back (which would queue behind a bulk D2H the caller may have in flight)."""
-    n = t.numel()
-    host = torch.empty((n,), dtype=torch.int64, pin_memory=True)
-    call("d4_publish_i64", ptr(t), n, host.data_ptr(), stream_ptr())
-    ev = torch.cuda.Event()
-    ev.record()
-    ev.synchronize()
-    return [int(x) for x in host.tolist()]
-
-
 @torch.no_grad()
 def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
               tiles_per_gauss: Optional[Tensor] = None, method: str = "auto"):
@@ -223,7 +211,7 @@ def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, ti
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     call("d4_exclusive_scan_i32", ptr(counts), n_seg, ptr(offsets), ptr(stats), ptr(ws), ws_bytes, st)
     stats[1] = counts[:n_seg].max() if n_seg > 0 else 0
-    n_isects, max_count = _read_back_i64(stats)  # the one device->host sync of the op
+    n_isects, max_count = (int(x) for x in stats.tolist())  # the one device->host sync of the op
     if n_isects >= 2 ** 31:
         raise _cabi.D4Error("more than 2^31 tile intersections")
     if max_count > _cabi.lib().d4_tile_sort_capacity():

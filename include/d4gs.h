@@ -190,12 +190,6 @@ int d4_camera_interp_fwd(const float *start6, const float *end6, int N, float *R
 int d4_camera_interp_bwd(const float *start6, const float *end6, int N, const float *v_RTs, float *v_start6,
                          float *v_end6, d4_stream_t stream);
 
-/* ---- host hand-over of the intersection count (the one device->host sync of a9) ---------------------
- * Stores n <= 32 int64 values from device memory into MAPPED PINNED host memory with a kernel (no copy-engine
- * transfer: a cudaMemcpy read-back would queue behind any bulk download the application has in flight).  The
- * caller records an event on `stream` after the call and waits on it before reading dst_host_mapped.       */
-int d4_publish_i64(const int64_t *src, int n, int64_t *dst_host_mapped, d4_stream_t stream);
-
 /* ---- a13: N-way combine of the sub-exposure renders -------------------------------------
  * replaces the stack/mean/max/min at scene_model.py:386-397: out = mean over N
  * of every channel, except channel max_ch (if >= 0) = max over N and channel
