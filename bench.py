@@ -329,12 +329,22 @@ def main():
     pending = [None, None]  # (event, keep-alive tensors) per buffer
     uploaded = {}           # step index -> (scene on the device, upload-done event)
 
+    # two persistent device copies of the inputs (no allocation in the loop; allocations made on a side stream
+    # are only recycled after cross-stream events and would otherwise hit cudaMalloc sporadically)
+    dev_sets = [type(sc)(**{kk: torch.empty_like(v, device=dev) for kk, v in host.items()}, width=W, height=H)
+                for _ in range(2)]
+    consumed = [None, None]  # event: the step that last read device set i has finished
+
     def upload(k):
+        i = k & 1
         with torch.cuda.stream(up_stream):
-            scn = type(sc)(**{kk: v.to(dev, non_blocking=True) for kk, v in host.items()}, width=W, height=H)
+            if consumed[i] is not None:
+                up_stream.wait_event(consumed[i])
+            for kk, v in host.items():
+                getattr(dev_sets[i], kk).copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(up_stream)
-        uploaded[k] = (scn, ev)
+        uploaded[k] = (dev_sets[i], ev)
 
     def e2e_step(k):
         if k not in uploaded:
@@ -343,8 +353,8 @@ def main():
         torch.cuda.current_stream().wait_event(ev)
         upload(k + 1)  # overlaps this step's kernels
         img, acc, grads = step(scn, want_outputs=True)
-        for t in scn.tensors().values():
-            t.record_stream(torch.cuda.current_stream())
+        consumed[k & 1] = torch.cuda.Event()
+        consumed[k & 1].record()
         outs = [img, acc] + grads
         buf = k & 1
         if out_host[buf] is None:
