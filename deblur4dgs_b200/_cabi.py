@@ -35,8 +35,8 @@ PROTOTYPES = {
     "d4_bucket_emit": (c_int, [P, P, P, I, I, I, I, I, P, P, P, P]),
     "d4_tile_sort": (c_int, [P, P, L, I, I, I, I, P, P, P]),
     "d4_tile_offsets": (c_int, [P, L, I, I, I, P, P]),
-    "d4_blend_fwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P]),
-    "d4_blend_bwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P, P, P, P, P, P]),
+    "d4_blend_fwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P]),
+    "d4_blend_bwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P, P, P, P, P, P, P]),
     "d4_deform_fwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P]),
     "d4_deform_bwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P]),
     "d4_compute_transforms_fwd": (c_int, [P, P, P, P, I, I, I, I, P, P]),

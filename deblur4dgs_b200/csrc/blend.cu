@@ -27,8 +27,9 @@
 namespace d4 {
 
 // ----------------------------------------------------------------------------- forward
-template <int D>
-__global__ void __launch_bounds__(kBlendThreads)
+// kMasks: also record, per intersection, which of the tile's 8 pixel blocks passed the alpha test (BlendArgs::hit_masks)
+template <int D, bool kMasks>
+__global__ void __launch_bounds__(kBlendThreads, (D <= 9 ? 5 : (D <= 17 ? 4 : 1)))
 blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restrict__ render_alphas,
                  int32_t *__restrict__ last_ids, float *__restrict__ acc_depth) {
     constexpr int DS = BlendCfg<D>::DS;
@@ -37,6 +38,7 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
     __shared__ float4 s_conic[kBatch];
     __shared__ __align__(16) float s_col[kBatch * (DS > DP ? DS : DP)];
     __shared__ uint32_t s_mask[kBatch];
+    __shared__ uint32_t s_hitw[kMasks ? kBlendThreads / 32 : 1][kBatch / 32];  // per warp: slots of the batch past the alpha test
 
     const int n_tiles = a.tile_w * a.tile_h;
     const int ct = blockIdx.x;
@@ -54,6 +56,16 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
     const int64_t range_start = a.tile_offsets[ct];
     const int64_t range_end = (ct == a.C * n_tiles - 1) ? a.n_isects : (int64_t)a.tile_offsets[ct + 1];
     const int num_batches = (int)((range_end - range_start + kBatch - 1) / kBatch);
+    // hit masks of a finished batch: thread t gathers bit (t & 31) of word (t >> 5) of every warp
+    auto write_hit_masks = [&](int64_t start, int size) {
+        if (tid < size) {
+            uint32_t m = 0u;
+#pragma unroll
+            for (int ww = 0; ww < kBlendThreads / 32; ++ww) m |= ((s_hitw[ww][tid >> 5] >> (tid & 31)) & 1u) << ww;
+            a.hit_masks[start + tid] = (uint8_t)m;
+        }
+    };
+    int prev_b = 0, prev_size = 0;  // last processed batch whose masks are still to be written
 
     float T = 1.0f;
     int32_t cur_idx = 0;
@@ -70,17 +82,28 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
     StagedRec<D> rec;
     stage_load<D>(rec, a, c, range_start + tid, num_batches > 0 && range_start + tid < range_end);
     for (int b = 0; b < num_batches; ++b) {
-        if (__syncthreads_count(done) >= kBlendThreads) break;
+        const bool all_done = __syncthreads_count(done) >= kBlendThreads;
+        if constexpr (kMasks) {
+            if (prev_size > 0) write_hit_masks(range_start + (int64_t)kBatch * prev_b, prev_size);
+            prev_size = 0;
+        }
+        if (all_done) break;
         const int64_t batch_start = range_start + (int64_t)kBatch * b;
         stage_store<D>(rec, tid, tx * kTile, ty * kTile, s_geom, s_conic, s_col, s_mask);
         __syncthreads();
+        if constexpr (kMasks) {
+            if (lane < kBatch / 32) s_hitw[w][lane] = 0u;
+            __syncwarp();
+        }
         const int batch_size = (int)min((int64_t)kBatch, range_end - batch_start);
         bool warp_done = __all_sync(0xffffffffu, done);
+        uint32_t hitbits = 0u;  // slots of the current 32-slot chunk with at least one pixel past the alpha test
         // one Gaussian of the hit list for this pixel; returns true when the whole warp is finished
         auto composite = [&](int t, float power, float L) -> bool {
             const float alpha = fminf(kAlphaMax, ex2_approx(power));
             const bool valid = !done && power <= L && alpha >= kAlphaMin;
             if (!__any_sync(0xffffffffu, valid)) return false;
+            if constexpr (kMasks) hitbits |= 1u << (t & 31);
             if (valid) {
                 const float next_T = T * (1.0f - alpha);
                 if (next_T <= kTMin) {
@@ -119,10 +142,25 @@ blend_fwd_kernel(BlendArgs a, float *__restrict__ render_colors, float *__restri
                 if (composite(ta, pa, ga.z)) { warp_done = true; break; }
                 if (has_b && composite(tb, pb, gb.z)) { warp_done = true; break; }
             }
+            if constexpr (kMasks) {
+                if (lane == 0) s_hitw[w][chunk] = hitbits;
+                hitbits = 0u;
+            }
+        }
+        if constexpr (kMasks) {
+            prev_b = b;
+            prev_size = batch_size;
         }
         {
             const int64_t next = batch_start + kBatch + tid;
             stage_load<D>(rec, a, c, next, b + 1 < num_batches && next < range_end);
+        }
+    }
+
+    if constexpr (kMasks) {
+        if (prev_size > 0) {  // masks of the last batch that was processed (prev_size is uniform for the CTA)
+            __syncthreads();
+            write_hit_masks(range_start + (int64_t)kBatch * prev_b, prev_size);
         }
     }
 
@@ -442,7 +480,8 @@ constexpr int kDefaultGpCfg = 0;
 template <int D>
 static int launch_fwd(const BlendArgs &a, float *rc, float *ra, int32_t *li, float *ad, cudaStream_t st) {
     int grid = a.C * a.tile_w * a.tile_h;
-    blend_fwd_kernel<D><<<grid, kBlendThreads, 0, st>>>(a, rc, ra, li, ad);
+    if (a.hit_masks) blend_fwd_kernel<D, true><<<grid, kBlendThreads, 0, st>>>(a, rc, ra, li, ad);
+    else blend_fwd_kernel<D, false><<<grid, kBlendThreads, 0, st>>>(a, rc, ra, li, ad);
     return 0;
 }
 // D4_BWD selects the backward formulation: "gp" = grouped (blend_bwd_gp.cu), "shfl" = warp-butterfly kernel below.
@@ -500,9 +539,9 @@ extern "C" int d4_blend_fwd(const float *means2d, const float *conics, const flo
                             int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets,
                             const int32_t *flatten_ids, int64_t n_isects, int normalize_depth,
                             float *render_colors, float *render_alphas, int32_t *last_ids, float *acc_depth,
-                            d4_stream_t stream) {
+                            uint8_t *hit_masks, d4_stream_t stream) {
     BlendArgs a{means2d, conics, opacities, colors, depths, backgrounds, colors_cam_stride, C, G, D0, width,
-                height, tile_w, tile_h, tile_offsets, flatten_ids, n_isects, normalize_depth};
+                height, tile_w, tile_h, tile_offsets, flatten_ids, n_isects, normalize_depth, hit_masks};
     if (int rc = check_blend_args("d4_blend_fwd", a, tile_size)) return rc;
     D4_CHECK_ARG(render_colors && render_alphas && last_ids, "d4_blend_fwd: null output");
     D4_CHECK_ARG(!normalize_depth || (depths && acc_depth), "d4_blend_fwd: normalize_depth needs depths and acc_depth");
@@ -527,9 +566,10 @@ extern "C" int d4_blend_bwd(const float *means2d, const float *conics, const flo
                             const float *render_alphas, const int32_t *last_ids, const float *acc_depth,
                             const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
                             float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
-                            d4_stream_t stream) {
+                            const uint8_t *hit_masks, d4_stream_t stream) {
     BlendArgs a{means2d, conics, opacities, colors, depths, backgrounds, colors_cam_stride, C, G, D0, width,
-                height, tile_w, tile_h, tile_offsets, flatten_ids, n_isects, normalize_depth};
+                height, tile_w, tile_h, tile_offsets, flatten_ids, n_isects, normalize_depth,
+                const_cast<uint8_t *>(hit_masks)};
     if (int rc = check_blend_args("d4_blend_bwd", a, tile_size)) return rc;
     D4_CHECK_ARG(render_alphas && last_ids && v_render_colors && v_render_alphas && v_means2d && v_conics &&
                      v_opacities && (v_colors || D0 == 0),

@@ -253,8 +253,12 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
         if (rel < SW) {
             const int tr = rel * 32 + lane;
             const int64_t bend = range_end - 1 - (int64_t)B * nbt;  // slot 0 = furthest back
-            stage_gaussian<D>(a, c, bend - tr, bend - tr >= range_start, tr, tx * kTile, ty * kTile, s_geom_all + buf * B,
-                              s_conic_all + buf * B, s_col_all + buf * B * DS, s_mask_all + buf * B);
+            const bool in_range = bend - tr >= range_start;
+            StagedRec<D> r0;
+            stage_load<D>(r0, a, c, bend - tr, in_range);
+            const int hm = (a.hit_masks && in_range) ? (int)a.hit_masks[bend - tr] : -1;
+            stage_store<D>(r0, tr, tx * kTile, ty * kTile, s_geom_all + buf * B, s_conic_all + buf * B,
+                           s_col_all + buf * B * DS, s_mask_all + buf * B, hm);
         }
     };
 
@@ -377,10 +381,12 @@ blend_bwd_gp_kernel(BlendArgs a, const float *__restrict__ render_alphas, const 
             StagedRec<D> rec;
             const bool stager = b + 1 < num_batches && tid < B;
             const int64_t bend = range_end - 1 - (int64_t)B * (b + 1);
-            stage_load<D>(rec, a, c, bend - tid, stager && bend - tid >= range_start);
+            const bool in_next = stager && bend - tid >= range_start;
+            stage_load<D>(rec, a, c, bend - tid, in_next);
+            const int hm = (a.hit_masks && in_next) ? (int)a.hit_masks[bend - tid] : -1;
             __syncthreads();  // every warp is done with this batch's buffer
             if (b + 1 < num_batches) {
-                if (stager) stage_store<D>(rec, tid, tx * kTile, ty * kTile, s_geom_all, s_conic_all, s_col_all, s_mask_all);
+                if (stager) stage_store<D>(rec, tid, tx * kTile, ty * kTile, s_geom_all, s_conic_all, s_col_all, s_mask_all, hm);
                 __syncthreads();
             }
         } else {

@@ -26,6 +26,11 @@ struct BlendArgs {
     const int32_t *tile_offsets, *flatten_ids;
     int64_t n_isects;
     int normalize_depth;
+    // optional [n_isects] bytes, written by the forward and read by the backward: bit w of entry i is set iff some
+    // pixel of warp w's 8x4 block passed the alpha test for intersection i in the forward.  The backward uses it in
+    // place of the (conservative, geometric) reach mask: same arithmetic in both directions, so no contributing
+    // pixel is lost, and the ~24 % of visits whose Gaussian touches a block's bounding box but no pixel disappear.
+    uint8_t *hit_masks;
 };
 
 // pixel owned by this thread: warp w -> 8x4 block (w&1, w>>1), lane -> (lane&7, lane>>3)
@@ -106,7 +111,8 @@ __device__ __forceinline__ void stage_load(StagedRec<D, kStageColors> &r, const 
 
 template <int D, bool kStageColors = true>
 __device__ __forceinline__ void stage_store(const StagedRec<D, kStageColors> &r, int tr, int tile_x0, int tile_y0,
-                                            float4 *s_geom, float4 *s_conic, float *s_col, uint32_t *s_mask) {
+                                            float4 *s_geom, float4 *s_conic, float *s_col, uint32_t *s_mask,
+                                            int given_mask = -1) {
     constexpr int DS = BlendCfg<D>::DS;
     if (r.g < 0) {
         s_mask[tr] = 0u;
@@ -115,11 +121,13 @@ __device__ __forceinline__ void stage_store(const StagedRec<D, kStageColors> &r,
     const float L = __log2f(r.op);
     s_geom[tr] = make_float4(r.x, r.y, L, __int_as_float(r.g));
     s_conic[tr] = make_float4(-0.5f * kLog2e * r.ca, -kLog2e * r.cb, -0.5f * kLog2e * r.cc, 1.0f / r.op);
-    // per-warp reach mask
+    // per-warp reach mask (or the forward's hit mask when the caller has one)
     uint32_t mask = 0u;
     const float tau = (L + kLog2_255) * kLn2;  // ln(255 * opacity)
     const float det = r.ca * r.cc - r.cb * r.cb;
-    if (!(det > 0.f) || !(r.ca > 0.f) || !(r.cc > 0.f)) {
+    if (given_mask >= 0) {
+        mask = (uint32_t)given_mask;
+    } else if (!(det > 0.f) || !(r.ca > 0.f) || !(r.cc > 0.f)) {
         mask = 0xffu;  // degenerate conic: no culling
     } else if (tau >= 0.f) {
         const float k = 2.0f * tau / det;

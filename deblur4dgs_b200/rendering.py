@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -31,6 +32,7 @@ from ._cabi import call, ptr, stream_ptr
 
 SUPPORTED_D = (1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32, 33)
 CHANNEL_CHUNK = 32
+HIT_MASKS = True  # forward records which 8x4 blocks pass the alpha test per intersection; the backward skips the rest
 BINNING_METHOD = "auto"  # "auto" | "bucket" | "radix" (see bin_tiles)
 
 
@@ -252,20 +254,24 @@ class _Blend(torch.autograd.Function):
         last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
         acc_depth = torch.empty((C, height, width), dtype=torch.float32, device=dev) if normalize_depth else None
         n_isects = flatten_ids.shape[0]
+        # per-intersection hit masks (which 8x4 pixel blocks passed the alpha test): the backward visits only those
+        needs_bwd = any(ctx.needs_input_grad[:5])
+        use_masks = needs_bwd and HIT_MASKS and os.environ.get("D4_HIT_MASKS", "1") != "0"
+        hit_masks = torch.zeros((n_isects,), dtype=torch.uint8, device=dev) if use_masks else None
         call("d4_blend_fwd", ptr(means2d), ptr(conics), ptr(opacities), ptr(colors), ccs, ptr(depths),
              ptr(backgrounds), C, G, D0, width, height, tile_size, tile_w, tile_h, ptr(isect_offsets),
              ptr(flatten_ids), n_isects, int(normalize_depth), ptr(render_colors), ptr(render_alphas), ptr(last_ids),
-             ptr(acc_depth), stream_ptr())
+             ptr(acc_depth), ptr(hit_masks), stream_ptr())
         # NOTE: render_colors is NOT saved -- the reference edits it in place (scene_model.py:391-393)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, flatten_ids,
-                              render_alphas, last_ids, acc_depth)
+                              render_alphas, last_ids, acc_depth, hit_masks)
         ctx.cfg = (C, G, D0, ccs, width, height, tile_size, tile_w, tile_h, n_isects, int(normalize_depth))
         return render_colors, render_alphas
 
     @staticmethod
     def backward(ctx, v_render_colors, v_render_alphas):
         (means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, flatten_ids, render_alphas, last_ids,
-         acc_depth) = ctx.saved_tensors
+         acc_depth, hit_masks) = ctx.saved_tensors
         C, G, D0, ccs, width, height, tile_size, tile_w, tile_h, n_isects, normalize_depth = ctx.cfg
         dev = means2d.device
         D = D0 + (1 if depths is not None else 0)
@@ -280,7 +286,7 @@ class _Blend(torch.autograd.Function):
              ptr(backgrounds), C, G, D0, width, height, tile_size, tile_w, tile_h, ptr(isect_offsets),
              ptr(flatten_ids), n_isects, normalize_depth, ptr(render_alphas), ptr(last_ids), ptr(acc_depth),
              ptr(v_rc), ptr(v_ra), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opacities), ptr(v_depths),
-             stream_ptr())
+             ptr(hit_masks), stream_ptr())
         v_backgrounds = None
         if backgrounds is not None and ctx.needs_input_grad[5]:
             # as gsplat: sum over pixels of v_colors * (1 - alpha); the depth channel has no background

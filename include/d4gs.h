@@ -118,14 +118,17 @@ int d4_tile_offsets(const int64_t *isect_ids_sorted, int64_t n_isects, int C, in
  * means2d [C,G,2], conics [C,G,3], opacities [G], colors [*,G,D0],
  * backgrounds [C,D0] or NULL.  D = D0 + (depths ? 1 : 0), 1 <= D <= 64.
  * out: render_colors [C,H,W,D], render_alphas [C,H,W], last_ids i32 [C,H,W],
- *      acc_depth [C,H,W] (un-normalised depth, only when normalize_depth).     */
+ *      acc_depth [C,H,W] (un-normalised depth, only when normalize_depth),
+ *      hit_masks u8 [n_isects] or NULL (caller zero-fills): bit w of entry i set iff some pixel of
+ *      the w-th 8x4 pixel block of the tile passed the alpha test for intersection i; hand it to
+ *      d4_blend_bwd, which then visits only those (block, Gaussian) pairs.          */
 int d4_blend_fwd(const float *means2d, const float *conics, const float *opacities,
                  const float *colors, int64_t colors_cam_stride, const float *depths,
                  const float *backgrounds, int C, int G, int D0, int width, int height,
                  int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets,
                  const int32_t *flatten_ids, int64_t n_isects, int normalize_depth,
                  float *render_colors, float *render_alphas, int32_t *last_ids, float *acc_depth,
-                 d4_stream_t stream);
+                 uint8_t *hit_masks, d4_stream_t stream);
 
 /* ---- a11: blend backward ------------------------------------------------------------
  * replaces gsplat.rasterize_to_pixels backward (and autograd of the depth
@@ -140,7 +143,7 @@ int d4_blend_bwd(const float *means2d, const float *conics, const float *opaciti
                  const float *render_alphas, const int32_t *last_ids, const float *acc_depth,
                  const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
                  float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
-                 d4_stream_t stream);
+                 const uint8_t *hit_masks /* from d4_blend_fwd, or NULL */, d4_stream_t stream);
 
 /* ---- a1-a6: motion-basis deformation at N sub-exposure timestamps ----------------------
  * replaces, fused: GaussianParams activations normalize(quats) / softmax(coefs)

@@ -47,7 +47,7 @@ def test_argument_errors_are_reported_not_thrown():
                    1, None, None, None, None, None, None)
     with pytest.raises(_cabi.D4Error, match="tile_size 16"):
         _cabi.call("d4_blend_fwd", None, None, None, None, 0, None, None, 1, 1, 3, 32, 32, 8, 4, 4, None, None, 0, 0,
-                   None, None, None, None, None)
+                   None, None, None, None, None, None)
 
 
 def test_no_cpu_fallback():

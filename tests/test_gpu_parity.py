@@ -106,32 +106,41 @@ def check_raster_against(name, inp, W, H, mode, ref, tol_img=1e-4, tol_grad=1e-4
     assert e_img <= tol_img, f"{name}: image rel err {e_img}"
     assert e_alpha <= tol_img, f"{name}: alpha rel err {e_alpha}"
     assert e_faint <= 1e-3, f"{name}: image rel err on faint pixels {e_faint}"
-    # ---- gradients: every backward blend formulation (D4_BWD is read per call by libd4gs.so)
-    meta["means2d"].retain_grad()
+    # ---- gradients: every backward blend formulation (D4_BWD is read per call by libd4gs.so); the grouped one
+    # both with the forward's hit masks (default) and with its own geometric reach masks (D4_HIT_MASKS=0 at forward)
     vc, va = T(ref["v_render_colors"]), T(ref["v_render_alphas"])
-    loss = (rc * vc).sum() + (ra * va).sum()
-    for bwd_mode in BWD_MODES:
-        kind, _, cfg = bwd_mode.partition(":")
-        os.environ["D4_BWD"] = kind
-        os.environ["D4_BWD_GP_CFG"] = cfg or "0"
-        for k in t:
-            t[k].grad = None
-        meta["means2d"].grad = None
-        try:
-            loss.backward(retain_graph=True)
-        finally:
-            os.environ.pop("D4_BWD", None)
-            os.environ.pop("D4_BWD_GP_CFG", None)
-        got = {k: t[k].grad.cpu().numpy() for k in t}
-        got["means2d"] = meta["means2d"].grad.cpu().numpy()
-        worst = {}
-        for k in ["means", "quats", "scales", "opacities", "colors", "viewmats", "backgrounds", "means2d"]:
-            r = ref["grad_" + k]
-            worst[k] = (scale_err(got[k], r), elem_q(got[k], r))
-        report(test=name, kind="grad", bwd=bwd_mode, **{k: v for k, v in worst.items()})
-        for k, (se, eq) in worst.items():
-            assert se <= tol_grad, f"{name} [{bwd_mode}]: grad {k} scale_err {se}"
-            assert eq <= 1e-2, f"{name} [{bwd_mode}]: grad {k} 99.9% element err {eq}"
+    for hit_masks in (True, False):
+        if not hit_masks:
+            os.environ["D4_HIT_MASKS"] = "0"
+            try:
+                t, rc, ra, meta = run_cuda_raster(inp, W, H, mode)
+            finally:
+                os.environ.pop("D4_HIT_MASKS", None)
+        meta["means2d"].retain_grad()
+        loss = (rc * vc).sum() + (ra * va).sum()
+        for bwd_mode in (BWD_MODES if hit_masks else BWD_MODES[:1]):
+            kind, _, cfg = bwd_mode.partition(":")
+            os.environ["D4_BWD"] = kind
+            os.environ["D4_BWD_GP_CFG"] = cfg or "0"
+            for k in t:
+                t[k].grad = None
+            meta["means2d"].grad = None
+            try:
+                loss.backward(retain_graph=True)
+            finally:
+                os.environ.pop("D4_BWD", None)
+                os.environ.pop("D4_BWD_GP_CFG", None)
+            got = {k: t[k].grad.cpu().numpy() for k in t}
+            got["means2d"] = meta["means2d"].grad.cpu().numpy()
+            worst = {}
+            for k in ["means", "quats", "scales", "opacities", "colors", "viewmats", "backgrounds", "means2d"]:
+                r = ref["grad_" + k]
+                worst[k] = (scale_err(got[k], r), elem_q(got[k], r))
+            tag = bwd_mode + ("" if hit_masks else ":reach-masks")
+            report(test=name, kind="grad", bwd=tag, **{k: v for k, v in worst.items()})
+            for k, (se, eq) in worst.items():
+                assert se <= tol_grad, f"{name} [{tag}]: grad {k} scale_err {se}"
+                assert eq <= 1e-2, f"{name} [{tag}]: grad {k} 99.9% element err {eq}"
 
 
 @pytest.mark.parametrize("fname", golden_files("raster_"))
