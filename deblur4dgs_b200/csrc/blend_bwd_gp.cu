@@ -24,8 +24,14 @@
 // shared with blend.cu; with NBUF = 2 it is double-buffered: batch b+1 is staged by a rotating set of
 // warps while the others already work on batch b, and there is ONE barrier per batch.
 //
+// The forward can hand over per-intersection HIT MASKS (BlendArgs::hit_masks: which of the tile's 8 pixel blocks
+// passed the alpha test); they are staged in place of the geometric reach masks, so a warp only visits Gaussians
+// that really contribute to one of its pixels.
+//
 // MEASURED at c3 (D = 17, 9 x 1.49 M intersections, B200; profiles/r01d_*): shuffle kernel 8.32 ms
-// (7.7e9 warp instructions, issue slots 80 % busy); this kernel: see launch_blend_bwd_gp below.
+// (7.7e9 warp instructions, issue slots 80 % busy); this kernel 6.19 ms with hit masks (4.3e9 warp instructions,
+// issue slots 60 % busy, ~20 % of the samples at the per-batch barrier), 6.81 ms with reach masks; the launch
+// shapes that were tried are listed at launch_blend_bwd_gp below and in profiles/r01d_bwd_experiments.md.
 #include <limits.h>
 
 #include <type_traits>
