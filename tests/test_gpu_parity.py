@@ -446,6 +446,33 @@ def test_full_size_c3_properties():
     mass = (o2["exposure_imgs"][..., :16].double().abs() * wgt.double().abs()).sum()
     assert abs(float(lin) - float(direct)) <= 1e-6 * float(mass)
     report(test="c3_properties", kind="props", n_isects=int(ids.numel()), lin=float(lin), direct=float(direct))
+    # at full size every backward formulation must agree: grouped + forward hit masks (default), grouped + geometric
+    # reach masks, warp-butterfly -- gradients of a random linear functional w.r.t. every leaf, <= 1e-5 of its scale
+    leaves = ["fg_means", "fg_quats", "motion_coefs", "rots", "transls"]
+    wa = torch.randn_like(o1["exposure_alphas"])
+
+    def grads_with(env):
+        for k, v in env.items():
+            os.environ[k] = v
+        try:
+            p = {k: getattr(s, k).clone().requires_grad_(True) for k in leaves}
+            cg = colors.clone().requires_grad_(True)
+            a2 = (p["fg_means"], p["fg_quats"], p["motion_coefs"], s.bg_means, s.bg_quats, p["rots"], p["transls"], s.times,
+                  s.RTs, scales, opac)
+            o = render_subexposures(*a2, cg, **kw)
+            ((o["exposure_imgs"][..., :16] * wgt).sum() + (o["exposure_alphas"] * wa).sum()).backward()
+            return {**{k: p[k].grad for k in leaves}, "colors": cg.grad}
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+
+    base = grads_with({})
+    for env in ({"D4_HIT_MASKS": "0"}, {"D4_BWD": "shfl"}):
+        other = grads_with(env)
+        for k, g0 in base.items():
+            dev_ = float((other[k] - g0).abs().max()) / (float(g0.abs().max()) + 1e-30)
+            report(test="c3_properties", kind="bwd_agreement", env=env, leaf=k, rel_dev=dev_)
+            assert dev_ <= 1e-5, f"{env} {k}: {dev_}"
 
 
 def test_camera_interpolation_a7():
