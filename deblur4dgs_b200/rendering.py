@@ -33,6 +33,7 @@ from ._cabi import call, ptr, stream_ptr
 SUPPORTED_D = (1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32, 33)
 CHANNEL_CHUNK = 32
 HIT_MASKS = True  # forward records which 8x4 blocks pass the alpha test per intersection; the backward skips the rest
+HIT_MASK_TAP = None  # tests set this to a list: every forward appends its hit-mask tensor (parity check against the oracle)
 BINNING_METHOD = "auto"  # "auto" | "bucket" | "radix" (see bin_tiles)
 
 
@@ -262,6 +263,8 @@ class _Blend(torch.autograd.Function):
              ptr(backgrounds), C, G, D0, width, height, tile_size, tile_w, tile_h, ptr(isect_offsets),
              ptr(flatten_ids), n_isects, int(normalize_depth), ptr(render_colors), ptr(render_alphas), ptr(last_ids),
              ptr(acc_depth), ptr(hit_masks), stream_ptr())
+        if HIT_MASK_TAP is not None:
+            HIT_MASK_TAP.append(hit_masks)
         # NOTE: render_colors is NOT saved -- the reference edits it in place (scene_model.py:391-393)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, flatten_ids,
                               render_alphas, last_ids, acc_depth, hit_masks)

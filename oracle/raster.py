@@ -164,6 +164,22 @@ def blend_fwd(means2d, conics, opacities, colors, backgrounds, width, height, ti
     return out, alphas, last_ids, edge
 
 
+def hit_masks(means2d, conics, opacities, width, height, tile_size, isect_offsets, flatten_ids):
+    """Per-intersection 8-bit block masks of the forward and a knife-edge flag per intersection
+    (orc_hit_masks).  means2d [C,G,2], conics [C,G,3], opacities [C,G]."""
+    means2d, conics, opacities = _f32(means2d), _f32(conics), _f32(opacities)
+    C = means2d.shape[0]
+    th, tw = isect_offsets.shape[1:]
+    flatten_ids = np.ascontiguousarray(flatten_ids, dtype=np.int32)
+    isect_offsets = np.ascontiguousarray(isect_offsets, dtype=np.int32)
+    n = flatten_ids.shape[0]
+    masks = np.zeros((n,), np.uint8)
+    edge = np.zeros((n,), np.uint8)
+    lib().orc_hit_masks(_p(means2d), _p(conics), _p(opacities), C, int(width), int(height), int(tile_size), int(tw),
+                        int(th), _p(isect_offsets), _p(flatten_ids), ctypes.c_int64(n), _p(masks), _p(edge))
+    return masks, edge
+
+
 def blend_bwd(means2d, conics, opacities, colors, backgrounds, width, height, tile_size,
               isect_offsets, flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas):
     means2d, conics, opacities, colors = _f32(means2d), _f32(conics), _f32(opacities), _f32(colors)

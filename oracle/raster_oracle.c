@@ -544,6 +544,51 @@ ORC_API void orc_blend_fwd(const float *means2d, const float *conics, const floa
     }
 }
 
+/*
+ * Per-intersection hit masks of the forward (the product's BlendArgs::hit_masks): bit w of hit_masks[idx] is set
+ * iff some pixel of the w-th 8x4 pixel block of the tile (w = (iy / 4) * 2 + ix / 8) reaches intersection idx
+ * before it has terminated and passes the alpha test there (the Gaussian that saturates a pixel counts: it is
+ * tested, not composited).  edge_isect[idx] = 1 where one of those decisions was within the knife-edge band.
+ * Same per-pixel walk as orc_blend_fwd; tile_size must be 16.  Both outputs zero-initialised by the caller.
+ */
+ORC_API void orc_hit_masks(const float *means2d, const float *conics, const float *opacities, int C, int width,
+                           int height, int tile_size, int tw, int th, const int32_t *tile_offsets,
+                           const int32_t *flatten_ids, int64_t n_isects, uint8_t *hit_masks, uint8_t *edge_isect) {
+    long n_tiles = (long)tw * th;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long ct = 0; ct < C * n_tiles; ++ct) {
+        int tile = (int)(ct % n_tiles);
+        int ty = tile / tw, tx = tile % tw;
+        int64_t start = tile_offsets[ct];
+        int64_t end = (ct == C * n_tiles - 1) ? n_isects : tile_offsets[ct + 1];
+        for (int iy = 0; iy < tile_size; ++iy)
+            for (int ix = 0; ix < tile_size; ++ix) {
+                int i = ty * tile_size + iy, j = tx * tile_size + ix;
+                if (i >= height || j >= width) continue;
+                const uint8_t bit = (uint8_t)(1u << ((iy / 4) * 2 + ix / 8));
+                float px = (float)j + 0.5f, py = (float)i + 0.5f;
+                float T = 1.0f;
+                for (int64_t idx = start; idx < end; ++idx) {
+                    int32_t g = flatten_ids[idx];
+                    float dx = means2d[2L * g] - px, dy = means2d[2L * g + 1] - py;
+                    float ca = conics[3L * g], cb = conics[3L * g + 1], cd = conics[3L * g + 2];
+                    float sigma = 0.5f * (ca * dx * dx + cd * dy * dy) + cb * dx * dy;
+                    float alpha = fminf(ALPHA_MAX, opacities[g] * expf(-sigma));
+                    if (fabsf(alpha - ALPHA_MIN) <= EDGE_REL * ALPHA_MIN * fmaxf(1.f, fabsf(sigma))) edge_isect[idx] = 1;
+                    if (sigma < 0.f || alpha < ALPHA_MIN) continue;
+                    hit_masks[idx] |= bit; /* one tile per thread: no race */
+                    float next_T = T * (1.0f - alpha);
+                    if (fabsf(next_T - T_MIN) <= 16.f * EDGE_REL * T_MIN) {
+                        /* the termination decision is on the knife edge: everything behind it may differ */
+                        for (int64_t r = idx; r < end; ++r) edge_isect[r] = 1;
+                    }
+                    if (next_T <= T_MIN) break;
+                    T = next_T;
+                }
+            }
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* blend backward (gsplat rasterize_to_pixels_bwd)                            */
 /* ------------------------------------------------------------------------ */
