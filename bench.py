@@ -40,18 +40,19 @@ UNIT = "frames/s"
 D0_SYNTH = 16  # rgb(3) + fg mask(1) + 4x3 track channels; +1 expected depth => D = 17 (scene_model.py:205-296)
 
 
-def measured_traffic(prefix):
-    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/traffic.json, written by scripts/ncu_summary.py); None when no capture matches."""
+def measured_capture(prefix):
+    """The committed ncu --set full capture of the dominant kernel (profiles/traffic.json, written by
+    scripts/ncu_summary.py): DRAM bytes, executed warp instructions and issue-slot utilisation of ONE launch;
+    ({}, None) when no capture matches."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
-        return None, None
+        return {}, None
     with open(p) as f:
         d = json.load(f)
     for k, v in d.items():
         if k.startswith(prefix):
-            return v.get("dram_bytes_per_launch"), f"{k} in profiles/traffic.json ({v.get('source')}, grid {v.get('grid')})"
-    return None, None
+            return v, f"{k} in profiles/traffic.json ({v.get('source')}, grid {v.get('grid')})"
+    return {}, None
 
 
 def peaks():
@@ -402,14 +403,27 @@ def main():
         tiles = math.ceil(W / 16) * math.ceil(H / 16)
         ab = algorithmic_bytes(sc.G, sc.num_fg, K, Dtot, P, I_frame, tiles)
         peak, peak_src = peaks()
-        dom = "d4_blend_bwd"
+        dom = "d4_blend_bwd_slab"
+        dom_kernel = f"blend_bwd_slab_kernel<{D0}, 1>"
         dom_ms = kernel_ms.get(dom, float("nan"))
-        traffic, traffic_src = measured_traffic(f"blend_bwd_gp_kernel<{Dtot}")
+        cap, cap_src = measured_capture(f"blend_bwd_slab_kernel<{D0}")
         if args.config != "c3" or world != 1 or args.checkpoint:
-            traffic, traffic_src = None, None  # the capture is of the c3 single-GPU launch
+            cap, cap_src = {}, None  # the capture is of the c3 single-GPU launch
+        traffic = cap.get("dram_bytes_per_launch")
         dom_bytes = ab["blend_bwd"] * frames_per_step_local
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         step_bytes = sum(ab.values()) * frames_per_step_local
+        # fp32-issue roofline of the same kernel ("report both rooflines for blend"): executed warp
+        # instructions of the captured launch against the chip's issue rate (SMs x 4 schedulers x 1 instruction / clock
+        # at the SM clock sampled during the timed region), with the live kernel time of this run
+        issue = None
+        if cap.get("inst_executed") and clocks and clocks.get("sm_mhz"):
+            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_issue = sm_count * 4 * clocks["sm_mhz"] * 1e6  # warp instructions / s
+            issue = {"inst_executed": cap["inst_executed"], "issue_active_pct_ncu": cap.get("issue_active_pct"),
+                     "achieved_ginst_s": cap["inst_executed"] / (dom_ms * 1e-3) / 1e9, "peak_ginst_s": peak_issue / 1e9,
+                     "frac": cap["inst_executed"] / (dom_ms * 1e-3) / peak_issue,
+                     "inst_per_isect": cap["inst_executed"] / max(1.0, I_total), "source": cap_src}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -417,12 +431,13 @@ def main():
             "data": "synthetic (seeded, SURVEY 8d); random-init scene, no dataset/checkpoint",
             "config": workload_config(args, sc),
             "n_isects_per_frame": I_frame,
-            "roofline": {"bound": "hbm", "kernel": f"blend_bwd_gp_kernel<{Dtot}> (d4_blend_bwd)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": f"{dom_kernel} ({dom})", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": traffic_src,
+                         "traffic_source": cap_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
-                         "note": "blend is fp32-issue / latency bound, not HBM bound (DESIGN.md); whole-step "
-                                 "algorithmic-bytes rate is in step_hbm"},
+                         "note": "blend is bound by fp32 issue + shared-memory wavefronts, not by HBM (DESIGN.md): see "
+                                 "roofline_issue; the whole-step algorithmic-bytes rate is in step_hbm"},
+            "roofline_issue": issue,
             "step_hbm": {"algorithmic_bytes_per_step": step_bytes,
                          "achieved_gbs": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                          "frac_of_peak": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak},

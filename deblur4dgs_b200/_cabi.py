@@ -36,7 +36,12 @@ PROTOTYPES = {
     "d4_tile_sort": (c_int, [P, P, L, I, I, I, I, P, P, P]),
     "d4_tile_offsets": (c_int, [P, L, I, I, I, P, P]),
     "d4_blend_fwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P]),
-    "d4_blend_bwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "d4_blend_bwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P, P, P, P, P, P, I, P]),
+    "d4_isect_pack": (c_int, [P, P, P, P, I, I, I, I, I, P, P, L, P, P, P]),
+    "d4_tile_sort_pack": (c_int, [P, P, L, I, I, I, I, P, P, P, P, P, P, I, I, P, P, P]),
+    "d4_slab_hit_words": (c_size_t, [L, L]),
+    "d4_blend_fwd_slab": (c_int, [P, P, P, P, L, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P]),
+    "d4_blend_bwd_slab": (c_int, [P, P, P, P, L, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P]),
     "d4_deform_fwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P]),
     "d4_deform_bwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P]),
     "d4_compute_transforms_fwd": (c_int, [P, P, P, P, I, I, I, I, P, P]),
@@ -68,7 +73,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if handle.d4_version() != 1:
+        if handle.d4_version() != 2:
             raise D4Error("libd4gs.so ABI version mismatch")
         _lib = handle
     return _lib

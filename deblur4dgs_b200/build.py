@@ -27,12 +27,14 @@ UNITS = {
     "binning.cu": [],
     "blend.cu": [],
     "blend_bwd_gp.cu": [],
+    "blend_slab_fwd.cu": [],
+    "blend_slab_bwd.cu": [],
     "deform.cu": [],
     "combine.cu": [],
     "camera.cu": [],
     "assemble.cu": [],
 }
-HEADERS = ["common.cuh", "blend_common.cuh", "project_math.cuh", "deform_math.cuh", "camera_math.cuh",
+HEADERS = ["common.cuh", "blend_common.cuh", "slab.cuh", "project_math.cuh", "deform_math.cuh", "camera_math.cuh",
            os.path.join("..", "..", "include", "d4gs.h")]
 
 

@@ -13,7 +13,7 @@
 // bulk-synchronous pass, so a scheduling surprise cannot hang the device.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "slab.cuh"
 
 namespace d4 {
 
@@ -325,16 +325,84 @@ bucket_emit_kernel(const float *__restrict__ means2d, const int32_t *__restrict_
     }
 }
 
+// ----------------------------------------------------------------------------- packed intersection records
+// Input of the slab blend kernels (slab.cuh): per intersection one 32-byte record with everything the per-pixel
+// evaluation needs, in the tile's depth order, records with an empty reach mask dropped.  One CTA per (camera, tile).
+struct PackArgs {
+    const float *means2d, *conics, *opacities, *depths;  // [C,G,2], [C,G,3], [G], [C,G] (depths may be null)
+    int G, tile_w, tile_size;
+    float4 *recs;         // [n_isects][2]
+    int32_t *rec_counts;  // [C * tiles]
+};
+
+template <typename IdAt>
+__device__ __forceinline__ void pack_segment(const PackArgs &p, IdAt id_at, int n, int32_t start, int64_t seg,
+                                             int n_tiles, int32_t *s_warp /*[blockDim / 32]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, n_warps = blockDim.x >> 5;
+    const int c = (int)(seg / n_tiles), tile = (int)(seg - (int64_t)c * n_tiles);
+    const int ty = tile / p.tile_w, tx = tile - ty * p.tile_w;
+    int run = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        bool keep = false;
+        if (i < n) {
+            const int32_t g = id_at(i);
+            const int32_t gl = g - c * p.G;
+            const float2 xy = __ldg(reinterpret_cast<const float2 *>(p.means2d) + g);
+            const float op = __ldg(p.opacities + gl);
+            const float *cp = p.conics + 3LL * g;
+            const float ca = __ldg(cp), cb = __ldg(cp + 1), cc = __ldg(cp + 2);
+            const float L = __log2f(op);
+            const uint32_t mask = reach_mask_of(xy.x, xy.y, L, ca, cb, cc, tx * p.tile_size, ty * p.tile_size);
+            keep = mask != 0u;
+            r0 = make_float4(xy.x, xy.y, L, __uint_as_float((uint32_t)gl | (mask << 24)));
+            r1 = make_float4(-0.5f * kLog2e * ca, -kLog2e * cb, -0.5f * kLog2e * cc, p.depths ? __ldg(p.depths + g) : 0.f);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int k = 0; k < n_warps; ++k) {
+            const int t = s_warp[k];
+            woff += k < w ? t : 0;
+            total += t;
+        }
+        if (keep) {
+            float4 *dst = p.recs + 2 * ((int64_t)start + run + woff + __popc(bal & ((1u << lane) - 1u)));
+            dst[0] = r0;
+            dst[1] = r1;
+        }
+        run += total;
+        __syncthreads();
+    }
+    if (tid == 0) p.rec_counts[seg] = run;
+}
+
+__global__ void __launch_bounds__(256)
+isect_pack_kernel(PackArgs p, const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                  int64_t n_isects, int64_t n_segments, int n_tiles) {
+    __shared__ int32_t s_warp[8];
+    const int64_t seg = blockIdx.x;
+    const int32_t start = tile_offsets[seg];
+    const int32_t end = (seg == n_segments - 1) ? (int32_t)n_isects : tile_offsets[seg + 1];
+    pack_segment(p, [&](int i) { return __ldg(flatten_ids + start + i); }, end - start, start, seg, n_tiles, s_warp);
+}
+
 __global__ void __launch_bounds__(256)
 tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__restrict__ tile_offsets, int64_t n_isects,
                  int64_t n_segments, int n_tiles, int tile_n_bits, int64_t *__restrict__ isect_ids,
-                 int32_t *__restrict__ flatten_ids) {
+                 int32_t *__restrict__ flatten_ids, PackArgs pack) {
     extern __shared__ uint64_t s_keys[];
+    __shared__ int32_t s_warp[8];
     const int64_t seg = blockIdx.x;
     const int32_t start = tile_offsets[seg];
     const int32_t end = (seg == n_segments - 1) ? (int32_t)n_isects : tile_offsets[seg + 1];
     const int n = end - start;
-    if (n <= 0) return;
+    if (n <= 0) {
+        if (pack.recs && threadIdx.x == 0) pack.rec_counts[seg] = 0;
+        return;
+    }
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
     for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[i] = i < n ? bucket_keys[start + i] : ~0ull;
@@ -380,6 +448,8 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
         flatten_ids[start + i] = (int32_t)(uint32_t)key;
         isect_ids[start + i] = hi_bits | (int64_t)(key >> 32);
     }
+    // packed records of the tile for the slab blend kernels, straight from the sorted keys in shared memory
+    if (pack.recs) pack_segment(pack, [&](int i) { return (int32_t)(uint32_t)s_keys[i]; }, n, start, seg, n_tiles, s_warp);
 }
 
 }  // namespace d4
@@ -411,6 +481,63 @@ extern "C" int d4_bucket_emit(const float *means2d, const int32_t *radii, const 
     return 0;
 }
 
+static int check_pack(const char *name, const float *means2d, const float *conics, const float *opacities, int G,
+                      int tile_size, float4 *recs, int32_t *rec_counts) {
+    D4_CHECK_ARG(means2d && conics && opacities && recs && rec_counts, "%s: null pointer", name);
+    D4_CHECK_ARG(G < (1 << 24), "%s: packed records hold 24-bit Gaussian ids (G = %d)", name, G);
+    D4_CHECK_ARG(tile_size == kTile, "%s: only tile_size 16 is built", name);
+    D4_CHECK_ARG(((uintptr_t)recs & 15) == 0 && ((uintptr_t)means2d & 7) == 0, "%s: misaligned pointer", name);
+    return 0;
+}
+
+extern "C" int d4_isect_pack(const float *means2d, const float *conics, const float *opacities, const float *depths,
+                             int C, int G, int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets,
+                             const int32_t *flatten_ids, int64_t n_isects, void *recs, int32_t *rec_counts,
+                             d4_stream_t stream) {
+    D4_CHECK_ARG(C >= 1 && tile_w >= 1 && tile_h >= 1 && n_isects >= 0 && tile_offsets && rec_counts, "d4_isect_pack: bad arguments");
+    if (n_isects == 0) {  // nothing to pack (the Gaussian arrays may be empty / null)
+        cudaMemsetAsync(rec_counts, 0, sizeof(int32_t) * (size_t)C * tile_w * tile_h, as_stream(stream));
+        return 0;
+    }
+    if (int rc = check_pack("d4_isect_pack", means2d, conics, opacities, G, tile_size, (float4 *)recs, rec_counts)) return rc;
+    D4_CHECK_ARG(flatten_ids || n_isects == 0, "d4_isect_pack: null pointer");
+    const int64_t n_seg = (int64_t)C * tile_w * tile_h;
+    PackArgs p{means2d, conics, opacities, depths, G, tile_w, tile_size, (float4 *)recs, rec_counts};
+    isect_pack_kernel<<<(unsigned)n_seg, 256, 0, as_stream(stream)>>>(p, tile_offsets, flatten_ids, n_isects, n_seg,
+                                                                      tile_w * tile_h);
+    D4_CHECK_LAUNCH("d4_isect_pack");
+    return 0;
+}
+
+extern "C" size_t d4_slab_hit_words(int64_t n_isects, int64_t n_segments) { return slab_hit_words(n_isects, n_segments); }
+
+extern "C" int d4_tile_sort_pack(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,
+                                 int tile_w, int tile_h, int max_count, int64_t *isect_ids, int32_t *flatten_ids,
+                                 const float *means2d, const float *conics, const float *opacities,
+                                 const float *depths, int G, int tile_size, void *recs, int32_t *rec_counts,
+                                 d4_stream_t stream) {
+    D4_CHECK_ARG(C >= 1 && tile_w >= 1 && tile_h >= 1 && n_isects >= 0, "d4_tile_sort_pack: bad arguments");
+    D4_CHECK_ARG(max_count <= kTileSortMax, "d4_tile_sort_pack: a tile holds %d intersections, capacity is %d "
+                                            "(use d4_isect_emit + d4_sort_pairs_u64 + d4_isect_pack)", max_count, kTileSortMax);
+    if (int rc = check_pack("d4_tile_sort_pack", means2d, conics, opacities, G, tile_size, (float4 *)recs, rec_counts)) return rc;
+    D4_CHECK_ARG(tile_offsets, "d4_tile_sort_pack: null pointer");
+    const int64_t n_seg = (int64_t)C * tile_w * tile_h;
+    if (n_isects == 0) {
+        cudaMemsetAsync(rec_counts, 0, sizeof(int32_t) * n_seg, as_stream(stream));
+        return 0;
+    }
+    D4_CHECK_ARG(bucket_keys && isect_ids && flatten_ids, "d4_tile_sort_pack: null pointer");
+    int n_pad = 1;
+    while (n_pad < max_count) n_pad <<= 1;
+    const size_t smem = sizeof(uint64_t) * (size_t)n_pad;
+    PackArgs p{means2d, conics, opacities, depths, G, tile_w, tile_size, (float4 *)recs, rec_counts};
+    tile_sort_kernel<<<(unsigned)n_seg, 256, smem, as_stream(stream)>>>(bucket_keys, tile_offsets, n_isects, n_seg,
+                                                                        tile_w * tile_h, d4_tile_n_bits(tile_w * tile_h),
+                                                                        isect_ids, flatten_ids, p);
+    D4_CHECK_LAUNCH("d4_tile_sort_pack");
+    return 0;
+}
+
 extern "C" int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,
                             int tile_w, int tile_h, int max_count, int64_t *isect_ids, int32_t *flatten_ids,
                             d4_stream_t stream) {
@@ -425,7 +552,7 @@ extern "C" int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_off
     const int64_t n_seg = (int64_t)C * tile_w * tile_h;
     tile_sort_kernel<<<(unsigned)n_seg, 256, smem, as_stream(stream)>>>(bucket_keys, tile_offsets, n_isects, n_seg,
                                                                         tile_w * tile_h, d4_tile_n_bits(tile_w * tile_h),
-                                                                        isect_ids, flatten_ids);
+                                                                        isect_ids, flatten_ids, PackArgs{});
     D4_CHECK_LAUNCH("d4_tile_sort");
     return 0;
 }

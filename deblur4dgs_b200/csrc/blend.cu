@@ -470,12 +470,10 @@ blend_bwd_kernel(BlendArgs a, const float *__restrict__ render_alphas, const int
     flush_acc(prev_size, s_gid[(num_batches & 1) ^ 1]);
 }
 
-// D4_BWD default: 1 = grouped backward (blend_bwd_gp.cu), 0 = shuffle kernel of this file (kept as the A/B
-// reference and as the second implementation the parity tests cross-check).  Two tensor-core formulations of the
-// colour-gradient contraction (3xTF32 mma.sync) were measured slower than both and removed: profiles/r01c_bwd_tc.md.
-constexpr int kDefaultBwdMode = 1;
-constexpr int kDefaultGpCfg = 0;
-
+// Two backward formulations: the grouped kernel of blend_bwd_gp.cu (default) and the shuffle kernel of this file (kept
+// as the A/B reference and as the second implementation the parity tests cross-check); the caller selects with the
+// bwd_mode argument of d4_blend_bwd.  Two tensor-core formulations of the colour-gradient contraction (3xTF32
+// mma.sync) were measured slower than both and removed: profiles/r01c_bwd_tc.md.
 // ----------------------------------------------------------------------------- dispatch
 template <int D>
 static int launch_fwd(const BlendArgs &a, float *rc, float *ra, int32_t *li, float *ad, cudaStream_t st) {
@@ -484,33 +482,19 @@ static int launch_fwd(const BlendArgs &a, float *rc, float *ra, int32_t *li, flo
     else blend_fwd_kernel<D, false><<<grid, kBlendThreads, 0, st>>>(a, rc, ra, li, ad);
     return 0;
 }
-// D4_BWD selects the backward formulation: "gp" = grouped (blend_bwd_gp.cu), "shfl" = warp-butterfly kernel below.
-// Read on every call so that one process can A/B the two (tests, scripts/ab_blend_bwd.py).
-static int bwd_mode() {
-    const char *e = getenv("D4_BWD");
-    if (!e) return kDefaultBwdMode;
-    return (e[0] == 's') ? 0 : 1;
-}
-static int bwd_gp_cfg() {
-    const char *e = getenv("D4_BWD_GP_CFG");
-    return e ? atoi(e) : kDefaultGpCfg;
-}
-
 template <int D>
-static int launch_bwd(const BlendArgs &a, const float *ra, const int32_t *li, const float *ad, const float *vrc,
-                      const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd, cudaStream_t st) {
+static int launch_bwd(int bwd_mode, const BlendArgs &a, const float *ra, const int32_t *li, const float *ad,
+                      const float *vrc, const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd,
+                      cudaStream_t st) {
     int grid = a.C * a.tile_w * a.tile_h;
-    if (bwd_mode() != 0) {
-        const int rc = launch_blend_bwd_gp(D, bwd_gp_cfg(), a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd, st);
+    if (bwd_mode == 0) {
+        const int rc = launch_blend_bwd_gp(D, a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd, st);
         if (rc >= 0) return rc;
     }
     constexpr size_t smem = BwdCfg<D>::smem_bytes();
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(blend_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return 1;
-        configured = true;
-    }
+    // the opt-in is per device: set it on every launch (a per-process flag would miss a second GPU)
+    if (cudaFuncSetAttribute(blend_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return 1;
     blend_bwd_kernel<D><<<grid, kBlendThreads, smem, st>>>(a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd);
     return 0;
 }
@@ -547,7 +531,13 @@ extern "C" int d4_blend_fwd(const float *means2d, const float *conics, const flo
     D4_CHECK_ARG(!normalize_depth || (depths && acc_depth), "d4_blend_fwd: normalize_depth needs depths and acc_depth");
     const int D = D0 + (depths ? 1 : 0);
     switch (D) {
-#define X(n) case n: launch_fwd<n>(a, render_colors, render_alphas, last_ids, acc_depth, as_stream(stream)); break;
+#define X(n)                                                                                                     \
+    case n:                                                                                                      \
+        if (launch_fwd<n>(a, render_colors, render_alphas, last_ids, acc_depth, as_stream(stream)) != 0) {       \
+            set_error("d4_blend_fwd: kernel configuration failed");                                              \
+            return 1;                                                                                            \
+        }                                                                                                        \
+        break;
         D4_FOR_EACH_D(X)
 #undef X
         default:
@@ -566,10 +556,11 @@ extern "C" int d4_blend_bwd(const float *means2d, const float *conics, const flo
                             const float *render_alphas, const int32_t *last_ids, const float *acc_depth,
                             const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
                             float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
-                            const uint8_t *hit_masks, d4_stream_t stream) {
+                            const uint8_t *hit_masks, int bwd_mode, d4_stream_t stream) {
     BlendArgs a{means2d, conics, opacities, colors, depths, backgrounds, colors_cam_stride, C, G, D0, width,
                 height, tile_w, tile_h, tile_offsets, flatten_ids, n_isects, normalize_depth,
                 const_cast<uint8_t *>(hit_masks)};
+    D4_CHECK_ARG(bwd_mode == 0 || bwd_mode == 1, "d4_blend_bwd: bwd_mode is 0 (grouped) or 1 (shuffle)");
     if (int rc = check_blend_args("d4_blend_bwd", a, tile_size)) return rc;
     D4_CHECK_ARG(render_alphas && last_ids && v_render_colors && v_render_alphas && v_means2d && v_conics &&
                      v_opacities && (v_colors || D0 == 0),
@@ -581,8 +572,11 @@ extern "C" int d4_blend_bwd(const float *means2d, const float *conics, const flo
     switch (D) {
 #define X(n)                                                                                                   \
     case n:                                                                                                    \
-        launch_bwd<n>(a, render_alphas, last_ids, acc_depth, v_render_colors, v_render_alphas, v_means2d,      \
-                      v_conics, v_colors, v_opacities, v_depths, as_stream(stream));                           \
+        if (launch_bwd<n>(bwd_mode, a, render_alphas, last_ids, acc_depth, v_render_colors, v_render_alphas,   \
+                          v_means2d, v_conics, v_colors, v_opacities, v_depths, as_stream(stream)) != 0) {     \
+            set_error("d4_blend_bwd: kernel configuration failed");                                            \
+            return 1;                                                                                          \
+        }                                                                                                      \
         break;
         D4_FOR_EACH_D(X)
 #undef X

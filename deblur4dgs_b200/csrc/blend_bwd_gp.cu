@@ -410,13 +410,10 @@ template <int D, int B, int NBUF, int MINB, int U, int GR, bool HL = (D <= 9)>
 static int launch_gp(const BlendArgs &a, const float *ra, const int32_t *li, const float *ad, const float *vrc,
                      const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd, cudaStream_t st) {
     constexpr size_t smem = GpCfg<D, B, NBUF, GR>::smem_bytes();
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(blend_bwd_gp_kernel<D, B, NBUF, MINB, U, GR, HL>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return 1;
-        configured = true;
-    }
+    // the opt-in is per device: set it on every launch (a per-process flag would miss a second GPU)
+    if (cudaFuncSetAttribute(blend_bwd_gp_kernel<D, B, NBUF, MINB, U, GR, HL>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return 1;
     const int grid = a.C * a.tile_w * a.tile_h;
     blend_bwd_gp_kernel<D, B, NBUF, MINB, U, GR, HL><<<grid, kBlendThreads, smem, st>>>(a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd);
     return 0;
@@ -438,13 +435,13 @@ constexpr int batch_for() {
     return best;
 }
 
-// launch configurations (cfg = D4_BWD_GP_CFG): 0 = single-buffered staging, largest batch for 3 CTAs / SM (default);
-// 1 = double-buffered staging, one barrier per batch; 2 = as 1 with an 8-row park tile and 4 CTAs / SM.
-// MEASURED at c3 (B200, N = 9 x 1.49 M intersections; blend_bwd ms): D = 17: cfg 0 7.04, cfg 1 7.53, cfg 2 8.31,
-// 8-row tile with 256-slot batches 7.70, compacted hit list 7.35; shuffle kernel (blend.cu) 8.32.
-// D = 5: cfg 0 4.22 (compacted hit list; 4.54 without), cfg 1 5.08, cfg 2 5.24; shuffle kernel 6.10.
-// Larger batches matter more than one barrier less (cfg 1 halves the batch), 16-row sweeps more than occupancy.
-int launch_blend_bwd_gp(int D, int cfg, const BlendArgs &a, const float *ra, const int32_t *li, const float *ad,
+// Launch shape: single-buffered staging, the largest batch that keeps 3 CTAs on an SM, 16-row park tile.
+// MEASURED at c3 (B200, N = 9 x 1.49 M intersections; blend_bwd ms, round 1): D = 17: this shape 7.04, double-buffered
+// staging with one barrier per batch 7.53, 8-row park tile with 4 CTAs / SM 8.31, 8-row tile with 256-slot batches
+// 7.70, compacted hit list 7.35; shuffle kernel (blend.cu) 8.32.  D = 5: 4.22 (compacted hit list; 4.54 without).
+// Larger batches matter more than one barrier less, 16-row sweeps more than occupancy (the other shapes were
+// removed in round 2; profiles/r01d_bwd_experiments.md keeps the numbers).
+int launch_blend_bwd_gp(int D, const BlendArgs &a, const float *ra, const int32_t *li, const float *ad,
                         const float *vrc, const float *vra, float *vm, float *vc, float *vcol, float *vo, float *vd,
                         cudaStream_t st) {
 #define GP_ARGS a, ra, li, ad, vrc, vra, vm, vc, vcol, vo, vd, st
@@ -452,8 +449,6 @@ int launch_blend_bwd_gp(int D, int cfg, const BlendArgs &a, const float *ra, con
 #define X(n)                                                                                          \
     case n:                                                                                           \
         if constexpr (n <= 17) {                                                                      \
-            if (cfg == 1) return launch_gp<n, batch_for<n, 2, 16, 3>(), 2, 3, 4, 16>(GP_ARGS);        \
-            if (cfg == 2) return launch_gp<n, batch_for<n, 2, 8, 4>(), 2, 4, 4, 8>(GP_ARGS);          \
             return launch_gp<n, batch_for<n, 1, 16, 3>(), 1, 3, 4, 16>(GP_ARGS);                      \
         } else {                                                                                      \
             return launch_gp<n, 128, 1, 1, 4, 16>(GP_ARGS);                                           \

@@ -2,8 +2,6 @@
 // tile / batch constants, the argument block, the per-thread pixel mapping and the staging of one
 // batch of Gaussians into shared memory (geometry pre-scaled to base 2, per-warp reach masks).
 #pragma once
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace d4 {
@@ -48,6 +46,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// Reach mask of one Gaussian for the tile whose first pixel is (tile_x0, tile_y0): bit w set iff the Gaussian can
+// reach alpha >= 1/255 on some pixel of warp w's 8x4 block.  The ellipse {sigma <= ln(255 o)} has the bounding box
+// |dx| <= sqrt(2 tau cov_xx), |dy| <= sqrt(2 tau cov_yy); the test is conservative (slack for rounding), so dropping
+// a Gaussian with an empty mask never changes a result.  Same arithmetic as stage_store below.
+__device__ __forceinline__ uint32_t reach_mask_of(float x, float y, float L, float ca, float cb, float cc, int tile_x0,
+                                                  int tile_y0) {
+    uint32_t mask = 0u;
+    const float tau = (L + kLog2_255) * kLn2;  // ln(255 * opacity)
+    const float det = ca * cc - cb * cb;
+    if (!(det > 0.f) || !(ca > 0.f) || !(cc > 0.f)) {
+        mask = 0xffu;  // degenerate conic: no culling
+    } else if (tau >= 0.f) {
+        const float k = 2.0f * tau / det;
+        const float ex = sqrtf(k * cc) * 1.0001f + 1e-3f;
+        const float ey = sqrtf(k * ca) * 1.0001f + 1e-3f;
+        const float rx = x - (float)tile_x0, ry = y - (float)tile_y0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float x0 = (float)((w & 1) * 8) + 0.5f, y0 = (float)((w >> 1) * 4) + 0.5f;
+            const bool hit = (rx >= x0 - ex) && (rx <= x0 + 7.0f + ex) && (ry >= y0 - ey) && (ry <= y0 + 3.0f + ey);
+            mask |= hit ? (1u << w) : 0u;
+        }
+    }
+    return mask;
 }
 
 // Stage one batch: thread tr loads Gaussian `idx` (if in range) into slot tr.
@@ -214,7 +238,7 @@ __device__ __forceinline__ void stage_gaussian(const BlendArgs &a, int c, int64_
 
 // blend_bwd_gp.cu: grouped backward (lane = pixel recurrence, lane = Gaussian accumulation).
 // Returns 0 when launched, -1 when D is not built, 1 on a CUDA configuration error.
-int launch_blend_bwd_gp(int D, int cfg, const BlendArgs &a, const float *render_alphas, const int32_t *last_ids,
+int launch_blend_bwd_gp(int D, const BlendArgs &a, const float *render_alphas, const int32_t *last_ids,
                         const float *acc_depth, const float *v_render_colors, const float *v_render_alphas,
                         float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
                         cudaStream_t stream);

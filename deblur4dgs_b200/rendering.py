@@ -21,7 +21,6 @@ from __future__ import annotations
 
 import ctypes
 import math
-import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -35,6 +34,12 @@ CHANNEL_CHUNK = 32
 HIT_MASKS = True  # forward records which 8x4 blocks pass the alpha test per intersection; the backward skips the rest
 HIT_MASK_TAP = None  # tests set this to a list: every forward appends its hit-mask tensor (parity check against the oracle)
 BINNING_METHOD = "auto"  # "auto" | "bucket" | "radix" (see bin_tiles)
+# "slab": packed per-tile record slabs streamed through an mbarrier ring by a producer warp (csrc/slab.cuh; default);
+# "direct": the gather-staged kernels of csrc/blend.cu / blend_bwd_gp.cu (kept as the second implementation the
+# parity tests cross-check)
+BLEND_PATH = "slab"
+BWD_MODE = 0  # direct path only: 0 = grouped backward kernel, 1 = warp-shuffle backward kernel
+SLAB_D0 = (4, 8, 16, 32)  # colour widths the slab kernels are built for (rasterization() pads)
 
 
 def _check_cuda(*ts):
@@ -189,23 +194,39 @@ def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height:
 
 @torch.no_grad()
 def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
-              tiles_per_gauss: Optional[Tensor] = None, method: str = "auto"):
+              tiles_per_gauss: Optional[Tensor] = None, method: str = "auto", pack=None):
     """Tile binning, both halves of SURVEY row a9 in one call: returns
     (isect_ids i64 [I], flatten_ids i32 [I], isect_offsets i32 [C,th,tw]) -- exactly what
     gsplat.isect_tiles + gsplat.isect_offset_encode produce.
 
     method "bucket": count per (camera, tile) -> scan (== offsets) -> emit into tile segments ->
     per-tile shared-memory sort; "radix": gsplat's structure (emit, global LSD radix sort, offset
-    encode); "auto": bucket unless a tile holds more entries than the shared-memory sort can take."""
+    encode); "auto": bucket unless a tile holds more entries than the shared-memory sort can take.
+
+    pack = (conics [C,G,3], opacities [G], blend_depths [C,G] | None): additionally build the packed record
+    slabs of the slab blend kernels (include/d4gs.h: d4_isect_pack) and return (..., recs, rec_counts)."""
     _check_cuda(means2d, radii, depths)
     C, G = radii.shape
     dev = means2d.device
     st = stream_ptr()
     n_seg = C * tile_width * tile_height
+
+    def packed(isect_ids, flatten_ids, offsets, recs=None, rec_counts=None):
+        if pack is None:
+            return isect_ids, flatten_ids, offsets
+        if recs is None:
+            conics, opacities, bdepths = pack
+            n = flatten_ids.shape[0]
+            recs = torch.empty((max(n, 1), 8), dtype=torch.float32, device=dev)
+            rec_counts = torch.empty((n_seg,), dtype=torch.int32, device=dev)
+            call("d4_isect_pack", ptr(means2d), ptr(conics), ptr(opacities), ptr(bdepths), C, G, tile_size, tile_width,
+                 tile_height, ptr(offsets), ptr(flatten_ids), n, ptr(recs), ptr(rec_counts), st)
+        return isect_ids, flatten_ids, offsets, recs, rec_counts
+
     if method == "radix":
         _, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
                                                 tiles_per_gauss=tiles_per_gauss)
-        return isect_ids, flatten_ids, isect_offset_encode(isect_ids, C, tile_width, tile_height)
+        return packed(isect_ids, flatten_ids, isect_offset_encode(isect_ids, C, tile_width, tile_height))
     counts = torch.zeros((n_seg + 1,), dtype=torch.int32, device=dev)  # last slot: scratch for the max
     call("d4_tile_count", ptr(means2d), ptr(radii), C, G, tile_size, tile_width, tile_height, ptr(counts), st)
     offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
@@ -220,18 +241,27 @@ def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, ti
     if max_count > _cabi.lib().d4_tile_sort_capacity():
         if method == "bucket":
             raise _cabi.D4Error(f"a tile holds {max_count} intersections: beyond the shared-memory sort capacity")
-        return bin_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss, method="radix")
+        return bin_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss, method="radix",
+                         pack=pack)
     isect_ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
     flatten_ids = torch.empty((n_isects,), dtype=torch.int32, device=dev)
     if n_isects == 0:
-        return isect_ids, flatten_ids, offsets
+        return packed(isect_ids, flatten_ids, offsets)
     keys = torch.empty((n_isects,), dtype=torch.int64, device=dev)
     cursors = torch.zeros((n_seg,), dtype=torch.int32, device=dev)
     call("d4_bucket_emit", ptr(means2d), ptr(radii), ptr(depths), C, G, tile_size, tile_width, tile_height,
          ptr(offsets), ptr(cursors), ptr(keys), st)
-    call("d4_tile_sort", ptr(keys), ptr(offsets), n_isects, C, tile_width, tile_height, max_count, ptr(isect_ids),
-         ptr(flatten_ids), st)
-    return isect_ids, flatten_ids, offsets
+    if pack is None:
+        call("d4_tile_sort", ptr(keys), ptr(offsets), n_isects, C, tile_width, tile_height, max_count, ptr(isect_ids),
+             ptr(flatten_ids), st)
+        return isect_ids, flatten_ids, offsets
+    conics, opacities, bdepths = pack
+    recs = torch.empty((n_isects, 8), dtype=torch.float32, device=dev)
+    rec_counts = torch.empty((n_seg,), dtype=torch.int32, device=dev)
+    call("d4_tile_sort_pack", ptr(keys), ptr(offsets), n_isects, C, tile_width, tile_height, max_count, ptr(isect_ids),
+         ptr(flatten_ids), ptr(means2d), ptr(conics), ptr(opacities), ptr(bdepths), G, tile_size, ptr(recs),
+         ptr(rec_counts), st)
+    return isect_ids, flatten_ids, offsets, recs, rec_counts
 
 
 # --------------------------------------------------------------------------- #
@@ -257,7 +287,7 @@ class _Blend(torch.autograd.Function):
         n_isects = flatten_ids.shape[0]
         # per-intersection hit masks (which 8x4 pixel blocks passed the alpha test): the backward visits only those
         needs_bwd = any(ctx.needs_input_grad[:5])
-        use_masks = needs_bwd and HIT_MASKS and os.environ.get("D4_HIT_MASKS", "1") != "0"
+        use_masks = needs_bwd and HIT_MASKS
         hit_masks = torch.zeros((n_isects,), dtype=torch.uint8, device=dev) if use_masks else None
         call("d4_blend_fwd", ptr(means2d), ptr(conics), ptr(opacities), ptr(colors), ccs, ptr(depths),
              ptr(backgrounds), C, G, D0, width, height, tile_size, tile_w, tile_h, ptr(isect_offsets),
@@ -289,12 +319,90 @@ class _Blend(torch.autograd.Function):
              ptr(backgrounds), C, G, D0, width, height, tile_size, tile_w, tile_h, ptr(isect_offsets),
              ptr(flatten_ids), n_isects, normalize_depth, ptr(render_alphas), ptr(last_ids), ptr(acc_depth),
              ptr(v_rc), ptr(v_ra), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opacities), ptr(v_depths),
-             ptr(hit_masks), stream_ptr())
+             ptr(hit_masks), int(BWD_MODE), stream_ptr())
         v_backgrounds = None
         if backgrounds is not None and ctx.needs_input_grad[5]:
             # as gsplat: sum over pixels of v_colors * (1 - alpha); the depth channel has no background
             v_backgrounds = (v_rc[..., :D0] * (1.0 - render_alphas)).sum(dim=(1, 2))
         return (v_means2d, v_conics, v_opacities, v_colors, v_depths, v_backgrounds, None, None, None, None, None, None)
+
+
+class _BlendSlab(torch.autograd.Function):
+    """Blend over the packed record slabs (csrc/slab.cuh).  means2d / conics / opacities / depths are inputs of the
+    autograd node only -- the kernels read their values from ``recs`` -- so that the gradients land where
+    gsplat's rasterize_to_pixels puts them."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, recs, rec_counts, width,
+                height, tile_size, normalize_depth):
+        _check_cuda(means2d, conics, opacities, colors, recs)
+        colors, backgrounds = _f32c(colors), _f32c(backgrounds)
+        C, G = means2d.shape[:2]
+        D0 = colors.shape[-1]
+        ccs = 0 if colors.dim() == 2 else G * D0
+        with_depth = depths is not None
+        D = D0 + int(with_depth)
+        dev = means2d.device
+        tile_h, tile_w = isect_offsets.shape[1:]
+        n_seg = C * tile_h * tile_w
+        render_colors = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
+        render_alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
+        last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+        acc_depth = torch.empty((C, height, width), dtype=torch.float32, device=dev) if normalize_depth else None
+        needs_bwd = any(ctx.needs_input_grad[:5])
+        hit_bits = None
+        if needs_bwd or HIT_MASK_TAP is not None:
+            words = _cabi.lib().d4_slab_hit_words(recs.shape[0], n_seg)
+            alloc = torch.zeros if HIT_MASK_TAP is not None else torch.empty  # every word the backward reads is written
+            hit_bits = alloc((words,), dtype=torch.int32, device=dev)
+        call("d4_blend_fwd_slab", ptr(recs), ptr(isect_offsets), ptr(rec_counts), ptr(colors), ccs, ptr(backgrounds), C, G,
+             D0, int(with_depth), width, height, tile_size, tile_w, tile_h, int(normalize_depth), ptr(render_colors),
+             ptr(render_alphas), ptr(last_ids), ptr(acc_depth), ptr(hit_bits), stream_ptr())
+        if HIT_MASK_TAP is not None:
+            HIT_MASK_TAP.append({"hit_bits": hit_bits, "recs": recs, "rec_counts": rec_counts,
+                                 "isect_offsets": isect_offsets, "last_ids": last_ids})
+        # NOTE: render_colors is NOT saved -- the reference edits it in place (scene_model.py:391-393)
+        ctx.save_for_backward(colors, backgrounds, isect_offsets, recs, rec_counts, render_alphas, last_ids, acc_depth,
+                              hit_bits)
+        ctx.cfg = (C, G, D0, ccs, width, height, tile_size, tile_w, tile_h, int(normalize_depth), with_depth,
+                   opacities.shape)
+        return render_colors, render_alphas
+
+    @staticmethod
+    def backward(ctx, v_render_colors, v_render_alphas):
+        colors, backgrounds, isect_offsets, recs, rec_counts, render_alphas, last_ids, acc_depth, hit_bits = ctx.saved_tensors
+        C, G, D0, ccs, width, height, tile_size, tile_w, tile_h, normalize_depth, with_depth, oshape = ctx.cfg
+        dev = colors.device
+        D = D0 + int(with_depth)
+        v_rc = _f32c(v_render_colors) if v_render_colors is not None else torch.zeros((C, height, width, D), device=dev)
+        v_ra = _f32c(v_render_alphas) if v_render_alphas is not None else torch.zeros((C, height, width, 1), device=dev)
+        # one zero-filled workspace for every accumulated gradient (a single memset instead of five)
+        n_m, n_c, n_col, n_o, n_d = C * G * 2, C * G * 3, colors.numel(), G, (C * G if with_depth else 0)
+        ws = torch.zeros((n_m + n_c + n_col + n_o + n_d,), dtype=torch.float32, device=dev)
+        v_means2d = ws[:n_m].view(C, G, 2)
+        v_conics = ws[n_m:n_m + n_c].view(C, G, 3)
+        v_colors = ws[n_m + n_c:n_m + n_c + n_col].view(colors.shape)
+        v_opacities = ws[n_m + n_c + n_col:n_m + n_c + n_col + n_o].view(oshape)
+        v_depths = ws[n_m + n_c + n_col + n_o:].view(C, G) if with_depth else None
+        call("d4_blend_bwd_slab", ptr(recs), ptr(isect_offsets), ptr(rec_counts), ptr(colors), ccs, ptr(backgrounds), C, G,
+             D0, int(with_depth), width, height, tile_size, tile_w, tile_h, normalize_depth, ptr(render_alphas),
+             ptr(last_ids), ptr(acc_depth), ptr(v_rc), ptr(v_ra), ptr(hit_bits), ptr(v_means2d), ptr(v_conics),
+             ptr(v_colors), ptr(v_opacities), ptr(v_depths), stream_ptr())
+        v_backgrounds = None
+        if backgrounds is not None and ctx.needs_input_grad[5]:
+            v_backgrounds = (v_rc[..., :D0] * (1.0 - render_alphas)).sum(dim=(1, 2))
+        return (v_means2d, v_conics, v_opacities, v_colors, v_depths, v_backgrounds, None, None, None, None, None, None,
+                None)
+
+
+def rasterize_slabs(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets, recs,
+                    rec_counts, backgrounds=None, depths=None, normalize_depth=False):
+    """Blend over packed record slabs (``bin_tiles(..., pack=...)``): the slab counterpart of
+    ``rasterize_to_pixels``.  ``colors`` [G,D0] / [C,G,D0] with D0 in SLAB_D0."""
+    if colors.shape[-1] not in SLAB_D0:
+        raise _cabi.D4Error(f"colour width {colors.shape[-1]} is not built for the slab path; rasterization() pads")
+    return _BlendSlab.apply(means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, recs, rec_counts,
+                            int(image_width), int(image_height), int(tile_size), bool(normalize_depth))
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets,
@@ -370,8 +478,18 @@ def rasterization(
         means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size)
     C = radii.shape[0]
     tile_width, tile_height = math.ceil(width / tile_size), math.ceil(height / tile_size)
-    isect_ids, flatten_ids, isect_offsets = bin_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
-                                                      tiles_per_gauss=tiles_per_gauss, method=BINNING_METHOD)
+    with_depth = render_mode in ("RGB+D", "RGB+ED", "D", "ED")
+    normalize = render_mode in ("RGB+ED", "ED")
+    blend_depths = depths if with_depth else None
+    slab = BLEND_PATH == "slab" and G < 2 ** 24
+    opac_c = _f32c(opacities)
+    if slab:
+        isect_ids, flatten_ids, isect_offsets, recs, rec_counts = bin_tiles(
+            means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss,
+            method=BINNING_METHOD, pack=(conics.detach(), opac_c.detach(), None if blend_depths is None else blend_depths.detach()))
+    else:
+        isect_ids, flatten_ids, isect_offsets = bin_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
+                                                          tiles_per_gauss=tiles_per_gauss, method=BINNING_METHOD)
 
     meta = {
         "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d, "depths": depths,
@@ -381,22 +499,33 @@ def rasterization(
         "tile_size": tile_size, "n_cameras": C,
     }
 
-    with_depth = render_mode in ("RGB+D", "RGB+ED", "D", "ED")
-    normalize = render_mode in ("RGB+ED", "ED")
     if render_mode in ("D", "ED"):
         colors = colors.new_zeros(colors.shape[:-1] + (0,))
         backgrounds = None if backgrounds is None else backgrounds.new_zeros(backgrounds.shape[:-1] + (0,))
     D0 = colors.shape[-1]
-    blend_depths = depths if with_depth else None
 
-    if D0 + int(with_depth) <= max(SUPPORTED_D) and D0 <= channel_chunk + 1:
-        colors_p, bg_p, pad = _pad_channels(colors, backgrounds, with_depth)
-        rc, render_alphas = rasterize_to_pixels(means2d, conics, colors_p, opacities, width, height, tile_size,
-                                                isect_offsets, flatten_ids, backgrounds=bg_p, depths=blend_depths,
-                                                normalize_depth=normalize)
+    def blend(col, bg, dd, norm):
+        """One blend call on <= channel_chunk colour channels (+ the depth channel when dd is given)."""
+        d0 = col.shape[-1]
+        if slab:
+            target = next(d for d in SLAB_D0 if d >= max(d0, 1))
+            pad = target - d0
+            if pad:
+                col = torch.cat([col, col.new_zeros(col.shape[:-1] + (pad,))], dim=-1)
+                bg = None if bg is None else torch.cat([bg, bg.new_zeros(bg.shape[:-1] + (pad,))], dim=-1)
+            rc, ra = rasterize_slabs(means2d, conics, col, opac_c, width, height, tile_size, isect_offsets, recs,
+                                     rec_counts, backgrounds=bg, depths=dd, normalize_depth=norm)
+        else:
+            col, bg, pad = _pad_channels(col, bg, dd is not None)
+            rc, ra = rasterize_to_pixels(means2d, conics, col, opacities, width, height, tile_size, isect_offsets,
+                                         flatten_ids, backgrounds=bg, depths=dd, normalize_depth=norm)
         if pad:
-            rc = torch.cat([rc[..., :D0], rc[..., D0 + pad:]], dim=-1)
-        render_colors = rc
+            rc = torch.cat([rc[..., :d0], rc[..., d0 + pad:]], dim=-1)
+        return rc, ra
+
+    max_d0 = max(SLAB_D0) if slab else max(SUPPORTED_D) - int(with_depth)
+    if D0 <= min(max_d0, channel_chunk + (0 if slab else 1)):
+        render_colors, render_alphas = blend(colors, backgrounds, blend_depths, normalize)
     else:
         # channel chunking, as gsplat does for > channel_chunk channels
         chunks, render_alphas = [], None
@@ -405,13 +534,7 @@ def rasterization(
             last = i == n_chunks - 1
             col = colors[..., i * channel_chunk:(i + 1) * channel_chunk]
             bg = None if backgrounds is None else backgrounds[..., i * channel_chunk:(i + 1) * channel_chunk]
-            dd = blend_depths if last else None
-            col_p, bg_p, pad = _pad_channels(col, bg, dd is not None)
-            rc, ra = rasterize_to_pixels(means2d, conics, col_p, opacities, width, height, tile_size, isect_offsets,
-                                         flatten_ids, backgrounds=bg_p, depths=dd,
-                                         normalize_depth=normalize and last)
-            if pad:
-                rc = torch.cat([rc[..., :col.shape[-1]], rc[..., col.shape[-1] + pad:]], dim=-1)
+            rc, ra = blend(col, bg, blend_depths if last else None, normalize and last)
             chunks.append(rc)
             render_alphas = ra if render_alphas is None else render_alphas
         render_colors = torch.cat(chunks, dim=-1)

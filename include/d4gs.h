@@ -35,7 +35,7 @@ extern "C" {
 
 typedef void *d4_stream_t; /* cudaStream_t */
 
-#define D4_ABI_VERSION 1
+#define D4_ABI_VERSION 2
 
 int d4_version(void);
 const char *d4_last_error(void);
@@ -143,7 +143,49 @@ int d4_blend_bwd(const float *means2d, const float *conics, const float *opaciti
                  const float *render_alphas, const int32_t *last_ids, const float *acc_depth,
                  const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
                  float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
-                 const uint8_t *hit_masks /* from d4_blend_fwd, or NULL */, d4_stream_t stream);
+                 const uint8_t *hit_masks /* from d4_blend_fwd, or NULL */,
+                 int bwd_mode /* 0 = grouped kernel (default), 1 = warp-shuffle kernel */, d4_stream_t stream);
+
+/* ---- a9 -> a10/a11: packed per-tile record slabs ("slab" path, the default of rasterization()) ----------
+ * The blend kernels' own input format, built once per forward from what gsplat.isect_tiles /
+ * isect_offset_encode produce: per intersection one 32-byte record
+ *     (x, y, log2(opacity), local id | reach mask << 24), (A', B', C', depth)
+ * with the conic pre-scaled to base 2, in the tile's depth order; records whose Gaussian cannot reach
+ * alpha >= 1/255 on any pixel of the tile are dropped, so tile t owns records
+ * [tile_offsets[t], tile_offsets[t] + rec_counts[t]).  recs: 32 * n_isects bytes, 16-byte aligned;
+ * rec_counts i32 [C*tile_h*tile_w].  G < 2^24.  depths may be NULL (depth field = 0).
+ * d4_tile_sort_pack = d4_tile_sort + d4_isect_pack in one kernel (ids still in shared memory).          */
+int d4_isect_pack(const float *means2d, const float *conics, const float *opacities, const float *depths,
+                  int C, int G, int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets,
+                  const int32_t *flatten_ids, int64_t n_isects, void *recs, int32_t *rec_counts,
+                  d4_stream_t stream);
+int d4_tile_sort_pack(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,
+                      int tile_w, int tile_h, int max_count, int64_t *isect_ids, int32_t *flatten_ids,
+                      const float *means2d, const float *conics, const float *opacities,
+                      const float *depths, int G, int tile_size, void *recs, int32_t *rec_counts,
+                      d4_stream_t stream);
+/* u32 words of the hit_bits buffer below: ((n_isects >> 5) + n_segments + 1) * 8 */
+size_t d4_slab_hit_words(int64_t n_isects, int64_t n_segments);
+
+/* a10 / a11 over the record slabs: same results as d4_blend_fwd / d4_blend_bwd (same per-pair arithmetic).
+ * One CTA per (camera, tile) = 8 consumer warps + 1 producer warp that streams the tile's records
+ * (cp.async.bulk) and colour rows (cp.async) through an mbarrier-synchronised shared-memory ring.
+ * colors [*,G,D0] with D0 in {4, 8, 16, 32}, 16-byte aligned; with_depth blends the records' depth field
+ * as channel D0.  last_ids index the RECORD list.  hit_bits (u32 [d4_slab_hit_words], may be NULL for a
+ * forward without backward): per (32-record chunk, 8x4 pixel block) which records passed the alpha test;
+ * the backward visits exactly those.  Gradients are accumulated with atomics: caller zero-fills.          */
+int d4_blend_fwd_slab(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
+                      const float *colors, int64_t colors_cam_stride, const float *backgrounds, int C, int G,
+                      int D0, int with_depth, int width, int height, int tile_size, int tile_w, int tile_h,
+                      int normalize_depth, float *render_colors, float *render_alphas, int32_t *last_ids,
+                      float *acc_depth, uint32_t *hit_bits, d4_stream_t stream);
+int d4_blend_bwd_slab(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
+                      const float *colors, int64_t colors_cam_stride, const float *backgrounds, int C, int G,
+                      int D0, int with_depth, int width, int height, int tile_size, int tile_w, int tile_h,
+                      int normalize_depth, const float *render_alphas, const int32_t *last_ids,
+                      const float *acc_depth, const float *v_render_colors, const float *v_render_alphas,
+                      const uint32_t *hit_bits, float *v_means2d, float *v_conics, float *v_colors,
+                      float *v_opacities, float *v_depths, d4_stream_t stream);
 
 /* ---- a1-a6: motion-basis deformation at N sub-exposure timestamps ----------------------
  * replaces, fused: GaussianParams activations normalize(quats) / softmax(coefs)

@@ -98,8 +98,13 @@ def _record_traffic(name, r, idx, units, src):
     key = f"{m.group(1)}<{m.group(2)}" if m else name
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
     d = json.load(open(path)) if os.path.exists(path) else {}
-    d[key] = {"dram_bytes_per_launch": tot, "ms": float(r[idx["gpu__time_duration.sum"]].replace(",", "")) if "gpu__time_duration.sum" in idx else None,
-              "source": os.path.basename(src), "grid": r[idx["launch__grid_size"]] if "launch__grid_size" in idx else None}
+    num = lambda k: float(r[idx[k]].replace(",", "")) if k in idx else None
+    d[key] = {"dram_bytes_per_launch": tot, "ms": num("gpu__time_duration.sum"),
+              "source": os.path.basename(src), "grid": r[idx["launch__grid_size"]] if "launch__grid_size" in idx else None,
+              # fp32-issue roofline of the blend kernels (SURVEY 8d asks for both rooflines)
+              "inst_executed": num("smsp__inst_executed.sum"),
+              "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+              "shared_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")}
     json.dump(d, open(path, "w"), indent=1, sort_keys=True)
 
 

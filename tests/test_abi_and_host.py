@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for name, n in fns.items():
         assert len(_cabi.PROTOTYPES[name][1]) == n, f"{name}: ctypes prototype has wrong arity"
     l = _cabi.lib()
-    assert l.d4_version() == 1
+    assert l.d4_version() == 2
     assert [l.d4_tile_n_bits(x) for x in (1, 2, 576, 1024, 3600)] == [1, 2, 10, 11, 12]
     assert l.d4_sort_workspace_bytes(1 << 20) >= 256 * 512 * 4
     assert l.d4_scan_workspace_bytes(300000) >= 8 * 147
