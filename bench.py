@@ -199,6 +199,9 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--shard", default="frames", choices=["frames", "subexposures"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync", action="store_true", help="gsplat-style binning with its device->host read-back every step "
+                                                        "(default: sync-free capacity mode, rendering.RenderCapacity)")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg of the resident measurement")
     ap.add_argument("--checkpoint", default=None, help="replay a reference checkpoint (trainer.py:126-140) instead of "
                                                        "the synthetic scene; --width/--height/--frame select the view")
     ap.add_argument("--width", type=int, default=None)
@@ -212,6 +215,7 @@ def main():
     import torch.distributed as dist
     from deblur4dgs_b200 import _cabi
     from deblur4dgs_b200.parallel import allreduce_sum_, render_frame_sharded, shard_indices
+    from deblur4dgs_b200.rendering import RenderCapacity
     from deblur4dgs_b200.scene import assemble_gaussians, render_subexposures
     from deblur4dgs_b200.synthetic import CONFIGS, make_config
 
@@ -248,6 +252,10 @@ def main():
     param_names = ["fg_means", "fg_quats", "fg_scales", "fg_colors", "fg_opacities", "motion_coefs", "bg_means",
                    "bg_quats", "bg_scales", "bg_colors", "bg_opacities", "rots", "transls"]
 
+    # sync-free tile binning: buffers sized by a learnt capacity, the intersection count never leaves the device inside
+    # a step (the first warm-up step synchronises once to learn the sizes; overflow is checked after the timed regions)
+    cap = None if args.sync else RenderCapacity()
+
     def step(scn, want_outputs=False):
         """One blurry frame forward + backward from the raw scene parameters."""
         p = {k: getattr(scn, k).detach().requires_grad_(True) for k in param_names}
@@ -260,17 +268,20 @@ def main():
         def local(times, RTs, combine):
             return render_subexposures(p["fg_means"], p["fg_quats"], p["motion_coefs"], p["bg_means"], p["bg_quats"],
                                        p["rots"], p["transls"], times, RTs, scales, opac, colors, scn.w2c, scn.K, W, H,
-                                       backgrounds=bg, render_mode="RGB+ED", combine=combine, ref_quirk=True)
+                                       backgrounds=bg, render_mode="RGB+ED", combine=combine, ref_quirk=True,
+                                       capacity=cap)
 
         if world > 1 and args.shard == "subexposures":
             def render_local(t, r):
                 o = local(t, r, False)
-                step.n_isects = int(o["meta"]["isect_ids"].numel())
+                if cap is None:
+                    step.n_isects = int(o["meta"]["isect_ids"].numel())
                 return o["exposure_imgs"], o["exposure_alphas"]
             img, acc = render_frame_sharded({}, scn.times, scn.RTs, render_local)
         else:
             o = local(scn.times, scn.RTs, True)
-            step.n_isects = int(o["meta"]["isect_ids"].numel())
+            if cap is None:
+                step.n_isects = int(o["meta"]["isect_ids"].numel())
             img, acc = o["img"], o["acc"]
         torch.autograd.backward([img, acc], [w_img, w_acc])
         grads = [p[k].grad for k in param_names]
@@ -288,6 +299,7 @@ def main():
     # ---- timed region 1: kernel-resident throughput (inputs already in HBM) ----------------
     prof = {}
     _cabi.PROFILE = prof  # per-C-ABI-call CUDA events on the launching stream (see _cabi.call)
+    _cabi.FILLS = 0       # torch-side zero-fill kernels issued by the op code
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -309,7 +321,37 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in prof.items()}
-    launches_per_step = sum(len(v) * _cabi.LAUNCHES.get(k, 1) for k, v in prof.items()) / args.steps
+    # every kernel of a step: the library's own (per C-ABI call) + the zero-fills of the op code (torch kernels)
+    own_launches_per_step = sum(len(v) * _cabi.LAUNCHES.get(k, 1) for k, v in prof.items()) / args.steps
+    fills_per_step = _cabi.FILLS / args.steps
+    launches_per_step = own_launches_per_step + fills_per_step
+    if cap is not None:
+        cap.check()  # raises if any timed step overflowed the binning capacity
+        step.n_isects = cap.last_n_isects
+
+    # ---- timed region 1b: the same steps replayed from ONE captured CUDA graph (no host work between kernels) ----
+    graph_ms = None
+    if world == 1 and cap is not None and not args.no_graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step(sc)  # allocator warm-up on the capture side stream
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step(sc)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            graph.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        cap.check()
+        graph_ms = g0.elapsed_time(g1) / args.steps
     n_sort_passes = math.ceil((32 + _cabi.lib().d4_tile_n_bits(math.ceil(W / 16) * math.ceil(H / 16)) +
                                int(math.floor(math.log2(frames_per_step_local))) + 1) / 8)
     if "d4_sort_pairs_u64" in prof:  # radix fallback only: 3 kernels per pass (the default bucketed binning has none)
@@ -446,6 +488,11 @@ def main():
                     "ms_per_step": float(ms2.item()) / args.steps},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "gpu_launches_per_step": launches_per_step,
+            "gpu_launches_detail": {"libd4gs_kernels_per_step": own_launches_per_step,
+                                    "torch_zero_fills_per_step": fills_per_step,
+                                    "host_syncs_per_step": 1 if cap is None else 0},
+            "graph": None if graph_ms is None else {"ms_per_step": graph_ms, "value": frames_per_step_global / (graph_ms * 1e-3),
+                                                    "note": "the same step (fwd+bwd) replayed from one captured CUDA graph"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -32,7 +32,10 @@ PROTOTYPES = {
     "d4_sort_pairs_u64": (c_int, [P, P, P, P, L, I, I, P, c_size_t, POINTER(c_int), P]),
     "d4_tile_sort_capacity": (c_int, []),
     "d4_tile_count": (c_int, [P, P, I, I, I, I, I, P, P]),
-    "d4_bucket_emit": (c_int, [P, P, P, I, I, I, I, I, P, P, P, P]),
+    "d4_bucket_emit": (c_int, [P, P, P, I, I, I, I, I, P, P, P, L, P]),
+    "d4_tile_sort_capacity_max": (c_int, []),
+    "d4_scan_counts": (c_int, [P, L, P, P, P, c_size_t, P]),
+    "d4_tile_sort_pack_cap": (c_int, [P, P, P, L, I, I, I, I, P, P, P, P, P, P, I, I, P, P, P, P]),
     "d4_tile_sort": (c_int, [P, P, L, I, I, I, I, P, P, P]),
     "d4_tile_offsets": (c_int, [P, L, I, I, I, P, P]),
     "d4_blend_fwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P]),
@@ -82,7 +85,15 @@ def lib():
 # bench.py sets PROFILE to a dict to collect (start, end) CUDA events around every C-ABI call on
 # the launching stream; LAUNCHES = kernels launched per call where that is not 1.
 PROFILE = None
-LAUNCHES = {"d4_deform_fwd": 2, "d4_deform_bwd": 2, "d4_exclusive_scan_i32": 2}
+LAUNCHES = {"d4_deform_fwd": 2, "d4_deform_bwd": 2, "d4_exclusive_scan_i32": 2, "d4_scan_counts": 2}
+
+
+FILLS = 0  # torch-side zero-fill kernels issued by the op code (counted so that bench.py reports every launch)
+
+
+def count_fill(n: int = 1):
+    global FILLS
+    FILLS += n
 
 
 def call(name: str, *args):
@@ -99,6 +110,23 @@ def call(name: str, *args):
     if rc != 0:
         msg = lib().d4_last_error()
         raise D4Error(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def check_tensors(*ts, what="deblur4dgs_b200 ops"):
+    """Every op enqueues on the CURRENT device's current stream: tensors must be CUDA tensors of that device
+    (there is no CPU fallback, and a launch on another device's stream would fault or race)."""
+    import torch
+    cur = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise D4Error(f"{what} need CUDA tensors: there is no CPU fallback")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise D4Error(f"{what}: tensor on cuda:{t.device.index} but the current device is cuda:{cur} "
+                          "(wrap the call in torch.cuda.device(...))")
 
 
 def ptr(t):

@@ -12,14 +12,13 @@ from __future__ import annotations
 import torch
 from torch import Tensor
 
-from ._cabi import D4Error, call, ptr, stream_ptr
+from ._cabi import D4Error, call, check_tensors, ptr, stream_ptr
 
 
 class _CameraInterp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, start6, end6, N):
-        if not start6.is_cuda:
-            raise D4Error("camera ops need CUDA tensors: there is no CPU fallback")
+        check_tensors(start6, end6, what="camera ops")
         s = start6.reshape(6).float().contiguous()
         e = end6.reshape(6).float().contiguous()
         RTs = torch.empty((N, 3, 4), dtype=torch.float32, device=s.device)
@@ -33,8 +32,8 @@ class _CameraInterp(torch.autograd.Function):
     def backward(ctx, v_RTs):
         s, e = ctx.saved_tensors
         vs, ve = torch.zeros_like(s), torch.zeros_like(e)
-        call("d4_camera_interp_bwd", ptr(s), ptr(e), ctx.N, ptr(v_RTs.float().contiguous()), ptr(vs), ptr(ve),
-             stream_ptr())
+        v = v_RTs.float().contiguous()  # bound to a name: must outlive the launch
+        call("d4_camera_interp_bwd", ptr(s), ptr(e), ctx.N, ptr(v), ptr(vs), ptr(ve), stream_ptr())
         return vs.reshape(ctx.shapes[0]), ve.reshape(ctx.shapes[1]), None
 
 

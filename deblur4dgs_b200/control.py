@@ -13,7 +13,7 @@ from typing import Dict, Optional, Tuple
 import torch
 from torch import Tensor
 
-from ._cabi import D4Error, call, ptr, stream_ptr
+from ._cabi import D4Error, call, check_tensors, ptr, stream_ptr
 
 
 @torch.no_grad()
@@ -23,8 +23,7 @@ def accumulate_densify_stats(running_stats: Dict[str, Tensor], means2d_grad: Ten
     """running_stats: {"xys_grad_norm_acc" f32 [G], "vis_count" i64 [G], "max_radii" f32 [G]} (trainer.py
     running_stats); means2d_grad [N,G,2]; radii int32 [N,G].  ``update_max_radii=False`` reproduces the
     reference literally: its ``index_put`` (no underscore, trainer.py:989) discards the maximum."""
-    if not means2d_grad.is_cuda:
-        raise D4Error("control ops need CUDA tensors: there is no CPU fallback")
+    check_tensors(means2d_grad, radii, what="control ops")
     g = means2d_grad.float().contiguous()
     r = radii.to(torch.int32).contiguous()
     N, G = r.shape

@@ -36,22 +36,39 @@ __device__ __forceinline__ int64_t block_sum_i64(int64_t v, int64_t *smem /*[8]*
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_block_sums_kernel(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ block_sums) {
+scan_block_sums_kernel(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ block_sums,
+                       int32_t *__restrict__ block_max /* nullable */) {
     __shared__ int64_t sm[kScanThreads / 32];
+    __shared__ int32_t smax[kScanThreads / 32];
     int64_t base = (int64_t)blockIdx.x * kScanTile;
     int64_t acc = 0;
+    int32_t mx = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {
         int64_t j = base + (int64_t)i * kScanThreads + threadIdx.x;
-        if (j < n) acc += in[j];
+        if (j < n) {
+            const int32_t v = in[j];
+            acc += v;
+            mx = max(mx, v);
+        }
     }
     int64_t t = block_sum_i64(acc, sm);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+    if (block_max) {
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < kScanThreads / 32; ++i) mx = max(mx, smax[i]);
+            block_max[blockIdx.x] = mx;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_apply_kernel(const int32_t *__restrict__ in, int64_t n, const int64_t *__restrict__ block_sums,
-                  int32_t *__restrict__ out, int64_t *__restrict__ total) {
+                  int32_t *__restrict__ out, int64_t *__restrict__ total, const int32_t *__restrict__ block_max,
+                  int64_t *__restrict__ max_out /* nullable: written by the last block */) {
     __shared__ int64_t sm[kScanThreads / 32];
     __shared__ int32_t warp_tot[kScanThreads / 32];
     // prefix of all earlier CTAs (each CTA re-reduces the short block_sums array)
@@ -86,7 +103,14 @@ scan_apply_kernel(const int32_t *__restrict__ in, int64_t n, const int64_t *__re
         if (base + i < n) out[base + i] = (int32_t)run;
         run += v[i];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total = run;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) {
+        *total = run;
+        if (max_out) {
+            int32_t mx = 0;
+            for (int j = 0; j < (int)gridDim.x; ++j) mx = max(mx, block_max[j]);
+            *max_out = mx;
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------- radix sort
@@ -259,7 +283,8 @@ tile_offsets_kernel(const int64_t *__restrict__ ids, int64_t n, int n_tiles, int
 //       (depth bits << 32 | flatten id) with a bitonic network and writes the final lists.
 // ~20-28 B of HBM traffic per intersection instead of 6 passes x 36 B.  The result is bit-identical
 // to the stable radix sort: ties in depth are ordered by flatten id, which is emission order.
-constexpr int kTileSortMax = 4096;  // segment capacity of the shared-memory sort (32 KB of keys)
+constexpr int kTileSortMax = 4096;      // segment capacity of the shared-memory sort without opt-in (32 KB of keys)
+constexpr int kTileSortMaxCap = 16384;  // with the > 48 KB dynamic shared memory opt-in (128 KB of keys)
 
 __device__ __forceinline__ void tile_rect_dev(float m2x, float m2y, int32_t radius, int tile_size, int tile_w,
                                               int tile_h, int &x0, int &y0, int &x1, int &y1) {
@@ -304,7 +329,7 @@ __global__ void __launch_bounds__(256)
 bucket_emit_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
                    const float *__restrict__ depths, int C, int G, int tile_size, int tile_w, int tile_h,
                    const int32_t *__restrict__ tile_offsets, int32_t *__restrict__ cursors,
-                   uint64_t *__restrict__ bucket_keys) {
+                   uint64_t *__restrict__ bucket_keys, int64_t capacity) {
     const int64_t tg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t idx = tg / kLanesPerGauss;
     const int sub = (int)(tg - idx * kLanesPerGauss);
@@ -321,7 +346,7 @@ bucket_emit_kernel(const float *__restrict__ means2d, const int32_t *__restrict_
         const int i = q / wx, j = q - i * wx;
         const int64_t t = cbase + (y0 + i) * tile_w + x0 + j;
         const int32_t pos = tile_offsets[t] + atomicAdd(cursors + t, 1);
-        bucket_keys[pos] = key;
+        if (pos < capacity) bucket_keys[pos] = key;  // beyond the caller's capacity: dropped, the overflow is flagged by the sort
     }
 }
 
@@ -391,14 +416,22 @@ isect_pack_kernel(PackArgs p, const int32_t *__restrict__ tile_offsets, const in
 
 __global__ void __launch_bounds__(256)
 tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__restrict__ tile_offsets, int64_t n_isects,
-                 int64_t n_segments, int n_tiles, int tile_n_bits, int64_t *__restrict__ isect_ids,
-                 int32_t *__restrict__ flatten_ids, PackArgs pack) {
+                 const int64_t *__restrict__ n_isects_dev, int64_t capacity, int sort_capacity,
+                 int64_t *__restrict__ overflow, int64_t n_segments, int n_tiles, int tile_n_bits,
+                 int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids, PackArgs pack) {
     extern __shared__ uint64_t s_keys[];
     __shared__ int32_t s_warp[8];
     const int64_t seg = blockIdx.x;
-    const int32_t start = tile_offsets[seg];
-    const int32_t end = (seg == n_segments - 1) ? (int32_t)n_isects : tile_offsets[seg + 1];
-    const int n = end - start;
+    // capacity mode (n_isects_dev != null): the intersection count lives on the device, the buffers hold `capacity`
+    // entries and the shared-memory sort `sort_capacity` keys; a tile that does not fit is dropped (no records) and
+    // *overflow is raised for the host to see later -- no device -> host sync inside the step
+    if (n_isects_dev) n_isects = *n_isects_dev;
+    const int64_t start64 = tile_offsets[seg];
+    const int64_t end64 = (seg == n_segments - 1) ? n_isects : (int64_t)tile_offsets[seg + 1];
+    const bool fits = end64 <= capacity && end64 - start64 <= sort_capacity;
+    if (!fits && overflow && threadIdx.x == 0) *overflow = 1;
+    const int32_t start = (int32_t)start64;
+    const int n = fits ? (int)(end64 - start64) : 0;
     if (n <= 0) {
         if (pack.recs && threadIdx.x == 0) pack.rec_counts[seg] = 0;
         return;
@@ -471,12 +504,13 @@ extern "C" int d4_tile_count(const float *means2d, const int32_t *radii, int C, 
 
 extern "C" int d4_bucket_emit(const float *means2d, const int32_t *radii, const float *depths, int C, int G,
                               int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets, int32_t *cursors,
-                              uint64_t *bucket_keys, d4_stream_t stream) {
+                              uint64_t *bucket_keys, int64_t capacity, d4_stream_t stream) {
+    D4_CHECK_ARG(capacity >= 0 && capacity < (1LL << 31), "d4_bucket_emit: bad capacity");
     D4_CHECK_ARG(C >= 1 && G >= 0 && (int64_t)C * G < (1LL << 32), "d4_bucket_emit: bad sizes");
     if (G == 0) return 0;
     D4_CHECK_ARG(means2d && radii && depths && tile_offsets && cursors && bucket_keys, "d4_bucket_emit: null pointer");
     bucket_emit_kernel<<<cdiv((int64_t)C * G * kLanesPerGauss, 256), 256, 0, as_stream(stream)>>>(
-        means2d, radii, depths, C, G, tile_size, tile_w, tile_h, tile_offsets, cursors, bucket_keys);
+        means2d, radii, depths, C, G, tile_size, tile_w, tile_h, tile_offsets, cursors, bucket_keys, capacity);
     D4_CHECK_LAUNCH("d4_bucket_emit");
     return 0;
 }
@@ -511,6 +545,26 @@ extern "C" int d4_isect_pack(const float *means2d, const float *conics, const fl
 
 extern "C" size_t d4_slab_hit_words(int64_t n_isects, int64_t n_segments) { return slab_hit_words(n_isects, n_segments); }
 
+static int launch_tile_sort(const char *name, const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects,
+                            const int64_t *n_isects_dev, int64_t capacity, int sort_capacity, int64_t *overflow, int C,
+                            int tile_w, int tile_h, int64_t *isect_ids, int32_t *flatten_ids, const PackArgs &p,
+                            cudaStream_t st) {
+    int n_pad = 1;
+    while (n_pad < sort_capacity) n_pad <<= 1;
+    const size_t smem = sizeof(uint64_t) * (size_t)n_pad;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_error("%s: cannot reserve %zu bytes of shared memory for the tile sort", name, smem);
+        return 1;
+    }
+    const int64_t n_seg = (int64_t)C * tile_w * tile_h;
+    tile_sort_kernel<<<(unsigned)n_seg, 256, smem, st>>>(bucket_keys, tile_offsets, n_isects, n_isects_dev, capacity, n_pad,
+                                                        overflow, n_seg, tile_w * tile_h, d4_tile_n_bits(tile_w * tile_h),
+                                                        isect_ids, flatten_ids, p);
+    D4_CHECK_LAUNCH(name);
+    return 0;
+}
+
 extern "C" int d4_tile_sort_pack(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,
                                  int tile_w, int tile_h, int max_count, int64_t *isect_ids, int32_t *flatten_ids,
                                  const float *means2d, const float *conics, const float *opacities,
@@ -527,15 +581,25 @@ extern "C" int d4_tile_sort_pack(const uint64_t *bucket_keys, const int32_t *til
         return 0;
     }
     D4_CHECK_ARG(bucket_keys && isect_ids && flatten_ids, "d4_tile_sort_pack: null pointer");
-    int n_pad = 1;
-    while (n_pad < max_count) n_pad <<= 1;
-    const size_t smem = sizeof(uint64_t) * (size_t)n_pad;
     PackArgs p{means2d, conics, opacities, depths, G, tile_w, tile_size, (float4 *)recs, rec_counts};
-    tile_sort_kernel<<<(unsigned)n_seg, 256, smem, as_stream(stream)>>>(bucket_keys, tile_offsets, n_isects, n_seg,
-                                                                        tile_w * tile_h, d4_tile_n_bits(tile_w * tile_h),
-                                                                        isect_ids, flatten_ids, p);
-    D4_CHECK_LAUNCH("d4_tile_sort_pack");
-    return 0;
+    return launch_tile_sort("d4_tile_sort_pack", bucket_keys, tile_offsets, n_isects, nullptr, n_isects, max_count, nullptr, C,
+                            tile_w, tile_h, isect_ids, flatten_ids, p, as_stream(stream));
+}
+
+extern "C" int d4_tile_sort_pack_cap(const uint64_t *bucket_keys, const int32_t *tile_offsets, const int64_t *bin_stats,
+                                     int64_t capacity, int sort_capacity, int C, int tile_w, int tile_h,
+                                     int64_t *isect_ids, int32_t *flatten_ids, const float *means2d, const float *conics,
+                                     const float *opacities, const float *depths, int G, int tile_size, void *recs,
+                                     int32_t *rec_counts, int64_t *overflow, d4_stream_t stream) {
+    D4_CHECK_ARG(C >= 1 && tile_w >= 1 && tile_h >= 1 && capacity >= 1 && capacity < (1LL << 31) && sort_capacity >= 1 &&
+                     sort_capacity <= kTileSortMaxCap,
+                 "d4_tile_sort_pack_cap: bad arguments (sort capacity <= %d)", kTileSortMaxCap);
+    if (int rc = check_pack("d4_tile_sort_pack_cap", means2d, conics, opacities, G, tile_size, (float4 *)recs, rec_counts)) return rc;
+    D4_CHECK_ARG(bucket_keys && tile_offsets && bin_stats && isect_ids && flatten_ids && overflow,
+                 "d4_tile_sort_pack_cap: null pointer");
+    PackArgs p{means2d, conics, opacities, depths, G, tile_w, tile_size, (float4 *)recs, rec_counts};
+    return launch_tile_sort("d4_tile_sort_pack_cap", bucket_keys, tile_offsets, 0, bin_stats, capacity, sort_capacity, overflow,
+                            C, tile_w, tile_h, isect_ids, flatten_ids, p, as_stream(stream));
 }
 
 extern "C" int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,
@@ -546,37 +610,46 @@ extern "C" int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_off
                                             "(use d4_isect_emit + d4_sort_pairs_u64)", max_count, kTileSortMax);
     if (n_isects == 0) return 0;
     D4_CHECK_ARG(bucket_keys && tile_offsets && isect_ids && flatten_ids, "d4_tile_sort: null pointer");
-    int n_pad = 1;
-    while (n_pad < max_count) n_pad <<= 1;
-    const size_t smem = sizeof(uint64_t) * (size_t)n_pad;
-    const int64_t n_seg = (int64_t)C * tile_w * tile_h;
-    tile_sort_kernel<<<(unsigned)n_seg, 256, smem, as_stream(stream)>>>(bucket_keys, tile_offsets, n_isects, n_seg,
-                                                                        tile_w * tile_h, d4_tile_n_bits(tile_w * tile_h),
-                                                                        isect_ids, flatten_ids, PackArgs{});
-    D4_CHECK_LAUNCH("d4_tile_sort");
-    return 0;
+    return launch_tile_sort("d4_tile_sort", bucket_keys, tile_offsets, n_isects, nullptr, n_isects, max_count, nullptr, C,
+                            tile_w, tile_h, isect_ids, flatten_ids, PackArgs{}, as_stream(stream));
 }
 
 extern "C" size_t d4_scan_workspace_bytes(int64_t n) {
-    return sizeof(int64_t) * (size_t)(cdiv(n > 0 ? n : 1, kScanTile) + 1);
+    const size_t nb = (size_t)cdiv(n > 0 ? n : 1, kScanTile);
+    return sizeof(int64_t) * (nb + 1) + sizeof(int32_t) * (nb + 2);  // block sums + block maxima
+}
+
+static int scan_i32(const char *name, const int32_t *in, int64_t n, int32_t *out_exclusive, int64_t *total, int64_t *max_out,
+                    void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    D4_CHECK_ARG(n >= 0 && total, "%s: bad arguments", name);
+    if (n == 0) {
+        cudaMemsetAsync(total, 0, sizeof(int64_t), st);
+        if (max_out) cudaMemsetAsync(max_out, 0, sizeof(int64_t), st);
+        return 0;
+    }
+    D4_CHECK_ARG(in && out_exclusive && workspace && workspace_bytes >= d4_scan_workspace_bytes(n),
+                 "%s: null pointer or workspace too small", name);
+    int nb = cdiv(n, kScanTile);
+    int64_t *bs = reinterpret_cast<int64_t *>(workspace);
+    int32_t *bm = reinterpret_cast<int32_t *>(bs + nb + 1);
+    scan_block_sums_kernel<<<nb, kScanThreads, 0, st>>>(in, n, bs, max_out ? bm : nullptr);
+    scan_apply_kernel<<<nb, kScanThreads, 0, st>>>(in, n, bs, out_exclusive, total, bm, max_out);
+    D4_CHECK_LAUNCH(name);
+    return 0;
 }
 
 extern "C" int d4_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out_exclusive, int64_t *total,
                                      void *workspace, size_t workspace_bytes, d4_stream_t stream) {
-    D4_CHECK_ARG(n >= 0 && total, "d4_exclusive_scan_i32: bad arguments");
-    if (n == 0) {
-        cudaMemsetAsync(total, 0, sizeof(int64_t), as_stream(stream));
-        return 0;
-    }
-    D4_CHECK_ARG(in && out_exclusive && workspace && workspace_bytes >= d4_scan_workspace_bytes(n),
-                 "d4_exclusive_scan_i32: null pointer or workspace too small");
-    int nb = cdiv(n, kScanTile);
-    int64_t *bs = reinterpret_cast<int64_t *>(workspace);
-    scan_block_sums_kernel<<<nb, kScanThreads, 0, as_stream(stream)>>>(in, n, bs);
-    scan_apply_kernel<<<nb, kScanThreads, 0, as_stream(stream)>>>(in, n, bs, out_exclusive, total);
-    D4_CHECK_LAUNCH("d4_exclusive_scan_i32");
-    return 0;
+    return scan_i32("d4_exclusive_scan_i32", in, n, out_exclusive, total, nullptr, workspace, workspace_bytes, as_stream(stream));
 }
+
+extern "C" int d4_scan_counts(const int32_t *counts, int64_t n, int32_t *offsets, int64_t *stats, void *workspace,
+                              size_t workspace_bytes, d4_stream_t stream) {
+    D4_CHECK_ARG(stats, "d4_scan_counts: null pointer");
+    return scan_i32("d4_scan_counts", counts, n, offsets, stats, stats + 1, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int d4_tile_sort_capacity_max(void) { return kTileSortMaxCap; }
 
 extern "C" size_t d4_sort_workspace_bytes(int64_t n) {
     int nb = cdiv(n > 0 ? n : 1, kSortTile);

@@ -282,7 +282,7 @@ int d4::check_slab_args(const char *name, const SlabArgs &a, int D0, int tile_si
     D4_CHECK_ARG(a.C >= 1 && a.G >= 0 && a.width > 0 && a.height > 0, "%s: bad sizes", name);
     D4_CHECK_ARG(a.tile_w == (a.width + kTile - 1) / kTile && a.tile_h == (a.height + kTile - 1) / kTile,
                  "%s: tile grid does not match the image size", name);
-    D4_CHECK_ARG(a.recs && a.tile_offsets && a.rec_counts && a.colors, "%s: null pointer", name);
+    D4_CHECK_ARG(a.recs && a.tile_offsets && a.rec_counts && (a.colors || a.G == 0), "%s: null pointer", name);
     D4_CHECK_ARG(D0 == 4 || D0 == 8 || D0 == 16 || D0 == 32, "%s: colour width %d not built (pad to 4, 8, 16 or 32)", name, D0);
     D4_CHECK_ARG(((uintptr_t)a.recs & 15) == 0 && ((uintptr_t)a.colors & 15) == 0 && (a.colors_cs & 3) == 0,
                  "%s: records and colours must be 16-byte aligned", name);

@@ -35,6 +35,27 @@ from .scene import render_subexposures
 NUM_SUBEXPOSURES = 11  # scene_model.py:248
 
 
+class SubexposureXys:
+    """Stands for ``info["means2d"]`` of ONE sub-exposure in the densifier side channel (scene_model.py:456-459).
+    The fused pass holds the screen-space centres of all N sub-exposures in one non-leaf tensor [N,G,2]; the trainer
+    reads ``_current_xys[ii].grad`` per sub-exposure (trainer.py:975), so ``.grad`` is that slice, [1,G,2]."""
+
+    def __init__(self, fused: Tensor, index: int):
+        self._fused, self._index = fused, index
+
+    @property
+    def grad(self) -> Optional[Tensor]:
+        g = self._fused.grad
+        return None if g is None else g[self._index:self._index + 1]
+
+    @property
+    def shape(self):
+        return torch.Size((1,) + tuple(self._fused.shape[1:]))
+
+    def detach(self) -> Tensor:
+        return self._fused.detach()[self._index:self._index + 1]
+
+
 # ------------------------------------------------------------------------------------------------ #
 # camera motion / exposure model (move_model.py:66-166)
 # ------------------------------------------------------------------------------------------------ #
@@ -132,6 +153,10 @@ class FrameRenderer(nn.Module):
         self.move_model = move_model if move_model is not None else CameraMotionModel()
         self.num_frames = rots.shape[1]
         self._current_xys = self._current_radii = self._current_img_wh = None
+        self._fused_xys = self._fused_radii = None
+        # sync-free tile binning: one RenderCapacity per (image size, sub-exposures, Gaussians) the renderer has seen
+        self.sync_free = True
+        self._capacities = {}
 
     @classmethod
     def from_scene(cls, scene, move_model: Optional[CameraMotionModel] = None) -> "FrameRenderer":
@@ -168,6 +193,20 @@ class FrameRenderer(nn.Module):
                                  self.bg["quats"], self.rots, self.transls, ts)
 
     # -- render -----------------------------------------------------------------------------------------
+    def _capacity_for(self, key):
+        if not self.sync_free:
+            return None
+        from .rendering import RenderCapacity
+        if key not in self._capacities:
+            self._capacities[key] = RenderCapacity()
+        return self._capacities[key]
+
+    def check_capacity(self):
+        """After a device synchronisation: raise if any sync-free render since the last check overflowed its
+        binning capacity (rendering.RenderCapacity.check)."""
+        for cap in self._capacities.values():
+            cap.check()
+
     def _subset(self, fg_only: bool, bg_only: bool):
         """Raw parameter groups of the rendered subset: (fg dict | None, bg dict | None)."""
         assert not (fg_only and bg_only)
@@ -202,8 +241,10 @@ class FrameRenderer(nn.Module):
             bg_color = torch.full((1, widths["img"]), bg_color, device=dev)
         bgc.append(bg_color)
         if return_mask:
+            # fg rows 1, bg rows 0 (scene_model.py:233-246); fg_only / bg_only render an all-ones mask, and a full render
+            # of a scene WITHOUT foreground Gaussians marks none (mask_values[:0] = 1 touches nothing)
             m = torch.ones(G, 1, device=dev)
-            if fg is not None and bg is not None:
+            if not fg_only and not bg_only:
                 m[n_fg:] = 0.0
             feats.append(m)
             bgc.append(torch.zeros(1, 1, device=dev))
@@ -239,12 +280,18 @@ class FrameRenderer(nn.Module):
             bg["means"] if bg is not None else None, bg["quats"] if bg is not None else None,
             self.rots, self.transls, times[0], RTs, torch.exp(cat("scales")), torch.sigmoid(cat("opacities")), colors,
             w2cs, Ks, W, H, backgrounds=backgrounds, render_mode="RGB+ED" if return_depth else "RGB",
-            combine=True, ref_quirk=True)
+            combine=True, ref_quirk=True, capacity=self._capacity_for((W, H, N, G)))
 
-        # densifier side channel (scene_model.py:456-461): one non-leaf tensor for all N sub-exposures
+        # densifier side channel (scene_model.py:456-461).  The reference stashes one means2d / radii tensor per
+        # sub-exposure and Trainer._prepare_control_step (trainer.py:967-989) indexes them: radii[ii] is [1,G],
+        # xys[ii].grad is [1,G,2].  Here they are per-sub-exposure views of the fused [N,G,.] tensors, which
+        # control.accumulate_densify_stats consumes whole (``_fused_xys`` / ``_fused_radii``).
         if out["means2d"].requires_grad:
             out["means2d"].retain_grad()
-            self._current_xys, self._current_radii, self._current_img_wh = out["means2d"], out["radii"], img_wh
+            self._fused_xys, self._fused_radii = out["means2d"], out["radii"]
+            self._current_xys = [SubexposureXys(out["means2d"], ii) for ii in range(N)]
+            self._current_radii = [out["radii"][ii:ii + 1] for ii in range(N)]
+            self._current_img_wh = img_wh
 
         res: Dict[str, Tensor] = {}
         pieces = torch.split(out["img"], list(widths.values()), dim=-1)

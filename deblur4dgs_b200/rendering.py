@@ -42,10 +42,86 @@ BWD_MODE = 0  # direct path only: 0 = grouped backward kernel, 1 = warp-shuffle 
 SLAB_D0 = (4, 8, 16, 32)  # colour widths the slab kernels are built for (rasterization() pads)
 
 
+class RenderCapacity:
+    """Buffer capacities for the sync-free ("capacity") mode of the tile binning.
+
+    gsplat sizes its intersection buffers by reading the intersection count back to the host inside every call
+    (``isect_tiles``); that read-back is the one device -> host sync of ``rasterization`` and it keeps the step from
+    being captured in a CUDA graph.  With a ``RenderCapacity`` the buffers are sized by a capacity instead
+    (``headroom`` x the largest count seen so far), the count stays on the device, and an overflow only raises a
+    device-side flag.  Counts and flag are copied to pinned host memory asynchronously after every binning;
+    ``poll()`` -- called at the start of the next render, never blocking -- adapts the capacity, and raises
+    ``D4Error`` if the previous render overflowed (its tiles beyond the capacity were rendered empty).  Use
+    ``check()`` after a ``torch.cuda.synchronize()`` for a definite answer, e.g. once per K steps.
+
+    The first render through a fresh object runs in the ordinary synchronising mode to learn the sizes."""
+
+    def __init__(self, headroom: float = 1.3):
+        self.headroom = float(headroom)
+        self.n_isects = 0   # capacity of the per-intersection buffers (0: not known yet)
+        self.sort_cap = 0   # capacity of the per-tile shared-memory sort
+        self.seen_isects = self.seen_tile = 0
+        self.overflowed = False
+        self._host = None   # pinned int64 [3]: n_isects, max per tile, overflow flag
+        self._event = None
+
+    @property
+    def ready(self) -> bool:
+        return self.n_isects > 0
+
+    def learn(self, n_isects: int, max_count: int):
+        self.seen_isects, self.seen_tile = max(self.seen_isects, n_isects), max(self.seen_tile, max_count)
+        cap_max = _cabi.lib().d4_tile_sort_capacity_max()
+        self.n_isects = max(self.n_isects, min(int(self.seen_isects * self.headroom) + 1024, 2 ** 31 - 1))
+        want = max(1024, int(self.seen_tile * 1.5))
+        sort_cap = 1
+        while sort_cap < want:
+            sort_cap <<= 1
+        self.sort_cap = max(self.sort_cap, min(sort_cap, cap_max))
+
+    def record(self, stats: Tensor):
+        """Enqueue the async copy of (n_isects, max per tile, overflow) to pinned memory."""
+        if self._host is None:
+            self._host = torch.zeros(3, dtype=torch.int64).pin_memory()
+        self._host.copy_(stats[:3], non_blocking=True)
+        if torch.cuda.is_current_stream_capturing():
+            self._event = None  # replayed with the graph: read with check() after a synchronize
+        else:
+            self._event = torch.cuda.Event()
+            self._event.record()
+
+    def _consume(self):
+        n, mx, ovf = (int(x) for x in self._host.tolist())
+        self.learn(n, mx)
+        if ovf:
+            self.overflowed = True
+            self._host[2] = 0
+            raise _cabi.D4Error(f"tile binning overflowed its capacity in a previous render ({n} intersections, {mx} in one "
+                                f"tile; that render dropped the tiles beyond it) -- capacity raised to {self.n_isects} / "
+                                f"{self.sort_cap}, render again")
+
+    @property
+    def last_n_isects(self) -> int:
+        """Intersection count of the last binning that poll() / check() has looked at (or of the learning render)."""
+        return int(self._host[0]) if self._host is not None and int(self._host[0]) > 0 else self.seen_isects
+
+    def poll(self):
+        """Non-blocking: look at the last finished binning, if any."""
+        if torch.cuda.is_current_stream_capturing():
+            return
+        if self._event is not None and self._event.query():
+            self._event = None
+            self._consume()
+
+    def check(self):
+        """After a device synchronisation: validate the last binning (also under CUDA graph replay)."""
+        if self._host is not None:
+            self._event = None
+            self._consume()
+
+
 def _check_cuda(*ts):
-    for t in ts:
-        if t is not None and not t.is_cuda:
-            raise _cabi.D4Error("deblur4dgs_b200 ops need CUDA tensors: the render path has no CPU fallback")
+    _cabi.check_tensors(*ts, what="deblur4dgs_b200 render ops")
 
 
 def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
@@ -107,15 +183,23 @@ class _Projection(torch.autograd.Function):
         means, quats, scales, viewmats, Ks, radii, conics = ctx.saved_tensors
         C, G, ms, qs, vs, ks, width, height, eps2d = ctx.cfg
         dev = means.device
-        zeros = lambda t: torch.zeros_like(t) if t is not None else torch.zeros((C, G), device=dev)
-        v_means2d = _f32c(v_means2d) if v_means2d is not None else torch.zeros_like(conics[..., :2]).contiguous()
-        v_depths = _f32c(v_depths) if v_depths is not None else torch.zeros((C, G), device=dev)
-        v_conics = _f32c(v_conics) if v_conics is not None else torch.zeros_like(conics)
-        v_means = torch.zeros_like(means)
-        v_quats = torch.zeros_like(quats)
-        v_scales = torch.zeros_like(scales)
+        z3 = 0
+        if v_means2d is None or v_depths is None or v_conics is None:  # an output nothing downstream used
+            v_means2d = _f32c(v_means2d) if v_means2d is not None else torch.zeros((C, G, 2), device=dev)
+            v_depths = _f32c(v_depths) if v_depths is not None else torch.zeros((C, G), device=dev)
+            v_conics = _f32c(v_conics) if v_conics is not None else torch.zeros((C, G, 3), device=dev)
+            z3 = 1
+        else:
+            v_means2d, v_depths, v_conics = _f32c(v_means2d), _f32c(v_depths), _f32c(v_conics)
         want_vm = ctx.needs_input_grad[3]
-        v_vm_full = torch.zeros((C, 4, 4), dtype=torch.float32, device=dev) if want_vm else None
+        # one zero-filled workspace for the accumulated outputs (a single memset instead of four)
+        n_m, n_q, n_s, n_v = means.numel(), quats.numel(), scales.numel(), (C * 16 if want_vm else 0)
+        ws = torch.zeros((n_m + n_q + n_s + n_v,), dtype=torch.float32, device=dev)
+        _cabi.count_fill(1 + z3)
+        v_means = ws[:n_m].view(means.shape)
+        v_quats = ws[n_m:n_m + n_q].view(quats.shape)
+        v_scales = ws[n_m + n_q:n_m + n_q + n_s].view(scales.shape)
+        v_vm_full = ws[n_m + n_q + n_s:].view(C, 4, 4) if want_vm else None
         call("d4_project_bwd", ptr(means), ms, ptr(quats), qs, ptr(scales), ptr(viewmats), vs, ptr(Ks), ks, C, G,
              width, height, eps2d, ptr(radii), ptr(conics), ptr(v_means2d), ptr(v_depths), ptr(v_conics),
              ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_vm_full), stream_ptr())
@@ -194,7 +278,8 @@ def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height:
 
 @torch.no_grad()
 def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
-              tiles_per_gauss: Optional[Tensor] = None, method: str = "auto", pack=None):
+              tiles_per_gauss: Optional[Tensor] = None, method: str = "auto", pack=None,
+              capacity: Optional["RenderCapacity"] = None):
     """Tile binning, both halves of SURVEY row a9 in one call: returns
     (isect_ids i64 [I], flatten_ids i32 [I], isect_offsets i32 [C,th,tw]) -- exactly what
     gsplat.isect_tiles + gsplat.isect_offset_encode produce.
@@ -204,7 +289,11 @@ def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, ti
     encode); "auto": bucket unless a tile holds more entries than the shared-memory sort can take.
 
     pack = (conics [C,G,3], opacities [G], blend_depths [C,G] | None): additionally build the packed record
-    slabs of the slab blend kernels (include/d4gs.h: d4_isect_pack) and return (..., recs, rec_counts)."""
+    slabs of the slab blend kernels (include/d4gs.h: d4_isect_pack) and return (..., recs, rec_counts).
+
+    capacity: a RenderCapacity -> sync-free mode once it has learnt the sizes (the first call synchronises):
+    isect_ids / flatten_ids / recs then hold ``capacity.n_isects`` entries, of which the first n_isects (a device
+    value) are meaningful."""
     _check_cuda(means2d, radii, depths)
     C, G = radii.shape
     dev = means2d.device
@@ -223,21 +312,52 @@ def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, ti
                  tile_height, ptr(offsets), ptr(flatten_ids), n, ptr(recs), ptr(rec_counts), st)
         return isect_ids, flatten_ids, offsets, recs, rec_counts
 
+    if capacity is not None and capacity.ready and pack is not None and method != "radix":
+        # ---- capacity mode: no device -> host read-back; one zero-filled int workspace (counts | cursors | stats)
+        capacity.poll()
+        lib = _cabi.lib()
+        cap = capacity.n_isects
+        izero = torch.zeros((2 * n_seg + 8,), dtype=torch.int32, device=dev)
+        _cabi.count_fill()
+        counts, cursors = izero[:n_seg], izero[n_seg:2 * n_seg]
+        stats = izero[2 * n_seg:2 * n_seg + 8].view(torch.int64)  # n_isects, max per tile, overflow, -
+        call("d4_tile_count", ptr(means2d), ptr(radii), C, G, tile_size, tile_width, tile_height, ptr(counts), st)
+        offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
+        ws_bytes = lib.d4_scan_workspace_bytes(n_seg)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        call("d4_scan_counts", ptr(counts), n_seg, ptr(offsets), ptr(stats), ptr(ws), ws_bytes, st)
+        isect_ids = torch.empty((cap,), dtype=torch.int64, device=dev)
+        flatten_ids = torch.empty((cap,), dtype=torch.int32, device=dev)
+        keys = torch.empty((cap,), dtype=torch.int64, device=dev)
+        call("d4_bucket_emit", ptr(means2d), ptr(radii), ptr(depths), C, G, tile_size, tile_width, tile_height,
+             ptr(offsets), ptr(cursors), ptr(keys), cap, st)
+        conics, opacities, bdepths = pack
+        recs = torch.empty((cap, 8), dtype=torch.float32, device=dev)
+        rec_counts = torch.empty((n_seg,), dtype=torch.int32, device=dev)
+        call("d4_tile_sort_pack_cap", ptr(keys), ptr(offsets), ptr(stats), cap, capacity.sort_cap, C, tile_width,
+             tile_height, ptr(isect_ids), ptr(flatten_ids), ptr(means2d), ptr(conics), ptr(opacities), ptr(bdepths), G,
+             tile_size, ptr(recs), ptr(rec_counts), ptr(stats[2:]), st)
+        capacity.record(stats)
+        return isect_ids, flatten_ids, offsets, recs, rec_counts
+
     if method == "radix":
         _, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
                                                 tiles_per_gauss=tiles_per_gauss)
         return packed(isect_ids, flatten_ids, isect_offset_encode(isect_ids, C, tile_width, tile_height))
-    counts = torch.zeros((n_seg + 1,), dtype=torch.int32, device=dev)  # last slot: scratch for the max
+    izero = torch.zeros((2 * n_seg + 8,), dtype=torch.int32, device=dev)  # counts | cursors | stats, one fill
+    _cabi.count_fill()
+    counts, cursors = izero[:n_seg], izero[n_seg:2 * n_seg]
+    stats = izero[2 * n_seg:2 * n_seg + 8].view(torch.int64)  # n_isects, max per tile
     call("d4_tile_count", ptr(means2d), ptr(radii), C, G, tile_size, tile_width, tile_height, ptr(counts), st)
     offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
-    stats = torch.empty((2,), dtype=torch.int64, device=dev)
     ws_bytes = _cabi.lib().d4_scan_workspace_bytes(n_seg)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    call("d4_exclusive_scan_i32", ptr(counts), n_seg, ptr(offsets), ptr(stats), ptr(ws), ws_bytes, st)
-    stats[1] = counts[:n_seg].max() if n_seg > 0 else 0
-    n_isects, max_count = (int(x) for x in stats.tolist())  # the one device->host sync of the op
+    call("d4_scan_counts", ptr(counts), n_seg, ptr(offsets), ptr(stats), ptr(ws), ws_bytes, st)
+    n_isects, max_count = (int(x) for x in stats[:2].tolist())  # the one device->host sync of the op
     if n_isects >= 2 ** 31:
         raise _cabi.D4Error("more than 2^31 tile intersections")
+    if capacity is not None:
+        capacity.learn(n_isects, max_count)
     if max_count > _cabi.lib().d4_tile_sort_capacity():
         if method == "bucket":
             raise _cabi.D4Error(f"a tile holds {max_count} intersections: beyond the shared-memory sort capacity")
@@ -248,9 +368,8 @@ def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, ti
     if n_isects == 0:
         return packed(isect_ids, flatten_ids, offsets)
     keys = torch.empty((n_isects,), dtype=torch.int64, device=dev)
-    cursors = torch.zeros((n_seg,), dtype=torch.int32, device=dev)
     call("d4_bucket_emit", ptr(means2d), ptr(radii), ptr(depths), C, G, tile_size, tile_width, tile_height,
-         ptr(offsets), ptr(cursors), ptr(keys), st)
+         ptr(offsets), ptr(cursors), ptr(keys), n_isects, st)
     if pack is None:
         call("d4_tile_sort", ptr(keys), ptr(offsets), n_isects, C, tile_width, tile_height, max_count, ptr(isect_ids),
              ptr(flatten_ids), st)
@@ -379,6 +498,7 @@ class _BlendSlab(torch.autograd.Function):
         # one zero-filled workspace for every accumulated gradient (a single memset instead of five)
         n_m, n_c, n_col, n_o, n_d = C * G * 2, C * G * 3, colors.numel(), G, (C * G if with_depth else 0)
         ws = torch.zeros((n_m + n_c + n_col + n_o + n_d,), dtype=torch.float32, device=dev)
+        _cabi.count_fill()
         v_means2d = ws[:n_m].view(C, G, 2)
         v_conics = ws[n_m:n_m + n_c].view(C, G, 3)
         v_colors = ws[n_m + n_c:n_m + n_c + n_col].view(colors.shape)
@@ -455,6 +575,7 @@ def rasterization(
     absgrad: bool = False,
     rasterize_mode: str = "classic",
     channel_chunk: int = CHANNEL_CHUNK,
+    capacity: Optional[RenderCapacity] = None,  # extension: sync-free binning (see RenderCapacity)
     **unsupported,
 ) -> Tuple[Tensor, Tensor, Dict]:
     """Drop-in for ``gsplat.rendering.rasterization`` (gsplat==1.1.1) as called at
@@ -486,7 +607,8 @@ def rasterization(
     if slab:
         isect_ids, flatten_ids, isect_offsets, recs, rec_counts = bin_tiles(
             means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss,
-            method=BINNING_METHOD, pack=(conics.detach(), opac_c.detach(), None if blend_depths is None else blend_depths.detach()))
+            method=BINNING_METHOD, pack=(conics.detach(), opac_c.detach(), None if blend_depths is None else blend_depths.detach()),
+            capacity=capacity)
     else:
         isect_ids, flatten_ids, isect_offsets = bin_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
                                                           tiles_per_gauss=tiles_per_gauss, method=BINNING_METHOD)

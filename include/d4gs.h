@@ -101,7 +101,8 @@ int d4_tile_count(const float *means2d, const int32_t *radii, int C, int G, int 
                   int tile_h, int32_t *tile_counts, d4_stream_t stream);
 int d4_bucket_emit(const float *means2d, const int32_t *radii, const float *depths, int C, int G,
                    int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets, int32_t *cursors,
-                   uint64_t *bucket_keys, d4_stream_t stream);
+                   uint64_t *bucket_keys, int64_t capacity /* entries of bucket_keys; writes beyond are dropped */,
+                   d4_stream_t stream);
 int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,
                  int tile_w, int tile_h, int max_count, int64_t *isect_ids, int32_t *flatten_ids,
                  d4_stream_t stream);
@@ -164,6 +165,21 @@ int d4_tile_sort_pack(const uint64_t *bucket_keys, const int32_t *tile_offsets, 
                       const float *means2d, const float *conics, const float *opacities,
                       const float *depths, int G, int tile_size, void *recs, int32_t *rec_counts,
                       d4_stream_t stream);
+/* Capacity mode: the binning without its device -> host read-back (gsplat.isect_tiles syncs to size its outputs;
+ * this variant is graph-capturable).  d4_scan_counts = d4_exclusive_scan_i32 that also leaves the largest count:
+ * stats[0] = total intersections, stats[1] = largest per-tile count (device int64).  d4_tile_sort_pack_cap reads
+ * the count from bin_stats[0] on the device; all per-intersection buffers hold `capacity` entries, the per-tile
+ * shared-memory sort `sort_capacity` keys (<= d4_tile_sort_capacity_max()).  A tile that does not fit is left
+ * without records and *overflow (device int64, caller zero-fills) is set to 1: the caller reads it whenever it
+ * next synchronises and re-renders with a larger capacity.                                                   */
+int d4_tile_sort_capacity_max(void);
+int d4_scan_counts(const int32_t *counts, int64_t n, int32_t *offsets, int64_t *stats, void *workspace,
+                   size_t workspace_bytes, d4_stream_t stream);
+int d4_tile_sort_pack_cap(const uint64_t *bucket_keys, const int32_t *tile_offsets, const int64_t *bin_stats,
+                          int64_t capacity, int sort_capacity, int C, int tile_w, int tile_h,
+                          int64_t *isect_ids, int32_t *flatten_ids, const float *means2d, const float *conics,
+                          const float *opacities, const float *depths, int G, int tile_size, void *recs,
+                          int32_t *rec_counts, int64_t *overflow, d4_stream_t stream);
 /* u32 words of the hit_bits buffer below: ((n_isects >> 5) + n_segments + 1) * 8 */
 size_t d4_slab_hit_words(int64_t n_isects, int64_t n_segments);
 

@@ -16,6 +16,16 @@ Run HERE (the authoring container), never on the GPU box:
    ``jaxtyping`` / ``cv2`` by empty placeholders (never called on this path).
    Gradients are torch autograd of that reference code for fixed cotangents.
 
+1b. ``scene_render.npz`` -- the reference's REAL ``SceneModel.render`` (scene_model.py:162-487: flag handling, feature
+   vector assembly, the loop over the 11 sub-exposures, the in-place combine, the densifier side channel, the
+   out_dict) and the reference's real ``MoveModel`` MLP / exposure code (move_model.py:66-135, 148-165), run on the
+   CPU.  What is substituted, because it is absent here: ``gsplat.rendering.rasterization`` by an autograd wrapper
+   around the oracle (oracle/raster.py), the pypose SE(3) interpolation inside ``forward_start_end_mid`` by
+   ``oracle/camera.py::camera_interp`` (both restatements: "parity unpinned" for those two), ``.cuda()`` by a
+   no-op, and the debug ``cv2.imwrite`` / ``os.makedirs`` to a hard-coded absolute path (scene_model.py:375-378)
+   by no-ops.  Also stored: the running stats the reference's ``Trainer._prepare_control_step`` loop
+   (trainer.py:967-989, restated literally) accumulates from that render.
+
 2. ``raster_*.npz`` -- produced by ``oracle/raster.py`` (the C oracle) on the
    seeded synthetic scenes.  These are NOT reference outputs (gsplat cannot be
    run here: "parity unpinned"); they freeze the oracle so that a later edit
@@ -164,6 +174,154 @@ def camera_golden():
     print("wrote camera_se3.npz", tuple(Rt.shape))
 
 
+class _CpuRasterization(torch.autograd.Function):
+    """gsplat.rendering.rasterization on the CPU through the oracle (forward + hand-derived backward).  The
+    screen-space gradient dL/dmeans2d -- what ``info["means2d"].grad`` holds in gsplat -- is parked in ``stash``."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, colors, backgrounds, viewmats, Ks, width, height, mode, stash):
+        from oracle import raster as orc
+        n = lambda t: t.detach().contiguous().numpy()
+        rc, ra, meta = orc.rasterization(n(means), n(quats), n(scales), n(opacities), n(colors), n(viewmats), n(Ks),
+                                         width, height, backgrounds=n(backgrounds), render_mode=mode)
+        ctx.meta, ctx.ra, ctx.stash = meta, ra, stash
+        stash["meta"] = meta
+        means2d = torch.from_numpy(meta["means2d"].copy())
+        ctx.mark_non_differentiable()
+        return torch.from_numpy(rc.copy()), torch.from_numpy(ra.copy()), means2d
+
+    @staticmethod
+    def backward(ctx, v_rc, v_ra, _v_means2d):
+        from oracle import raster as orc
+        g = orc.rasterization_backward(ctx.meta, ctx.ra, v_rc.contiguous().numpy(), v_ra.contiguous().numpy(),
+                                       want_viewmats=False)
+        ctx.stash["means2d_grad"] = torch.from_numpy(np.asarray(g["means2d"], np.float32).copy())
+        t = lambda k: torch.from_numpy(np.asarray(g[k], np.float32).copy())
+        return (t("means"), t("quats"), t("scales"), t("opacities"), t("colors"), None, None, None, None, None, None,
+                None)
+
+
+def scene_render_golden():
+    GaussianParams, MotionBases, SceneModel = _import_reference()
+    import flow3d.scene_model as sm_mod
+    import flow3d.models.move_model as mm_mod
+    from oracle import camera as ocam
+    from oracle import raster as orc
+    orc.set_num_threads(8)
+
+    stashes = []
+
+    def rasterization(means, quats, scales, opacities, colors, backgrounds, viewmats, Ks, width, height, packed=False,
+                      render_mode="RGB"):
+        assert packed is False
+        stash = {}
+        stashes.append(stash)
+        rc, ra, means2d = _CpuRasterization.apply(means, quats, scales, opacities, colors, backgrounds, viewmats, Ks,
+                                                  width, height, render_mode, stash)
+        info = {"means2d": means2d, "radii": torch.from_numpy(stash["meta"]["radii"].copy()), "width": width,
+                "height": height}
+        return rc, ra, info
+
+    def forward_start_end_mid(self, info, num_cameras=10, mode="uniform", stage="second"):
+        """move_model.py:138-166 with the pypose calls (:145-146) replaced by oracle/camera.py::camera_interp."""
+        R, T, time = info["R"], info["T"], info["timestep"]
+        RT_start, RT_end, time_start, time_end = self.forward(R, T, time, stage=stage)
+        RTs = ocam.camera_interp(RT_start[0], RT_end[0], num_cameras)
+        num_fg = time_start.shape[0]
+        time_start = time_start.unsqueeze(-1).repeat(1, num_cameras)
+        time_end = time_end.unsqueeze(-1).repeat(1, num_cameras)
+        weights = (torch.arange(num_cameras) / (num_cameras - 1)).to(RTs.device)
+        weights = weights.unsqueeze(0).repeat(num_fg, 1)
+        times = (time_start + time) * (1. - weights) + (time_end + time) * weights
+        times = times.reshape(num_fg, num_cameras)
+        deltaT = torch.abs(time_end[:, num_cameras - 1:])
+        return RTs, times, deltaT
+
+    sm_mod.rasterization = rasterization
+    sm_mod.cv2 = types.SimpleNamespace(imwrite=lambda *a, **k: True)
+    sm_mod.os = types.SimpleNamespace(makedirs=lambda *a, **k: None, path=os.path)
+    mm_mod.MoveModel.forward_start_end_mid = forward_start_end_mid
+    cuda0 = torch.nn.Module.cuda
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        W, H, t_frame = 64, 48, 3
+        sc = make_scene(G=1500, width=W, height=H, K=5, N=3, seed=55, scale_mult=2.5)
+        fg = GaussianParams(sc.fg_means, sc.fg_quats, sc.fg_scales, sc.fg_colors, sc.fg_opacities, motion_coefs=sc.motion_coefs)
+        bg = GaussianParams(sc.bg_means, sc.bg_quats, sc.bg_scales, sc.bg_colors, sc.bg_opacities)
+        mb = MotionBases(sc.rots, sc.transls)
+        model = SceneModel(sc.K, sc.w2c, fg, mb, bg)
+    finally:
+        torch.nn.Module.cuda = cuda0
+    torch.manual_seed(3)
+    with torch.no_grad():  # non-trivial camera deltas and exposure (the heads are zero-initialised)
+        for head in (model.move_model.RT_head0, model.move_model.RT_head1):
+            head[-1].bias.copy_(0.01 * torch.randn(6))
+        model.move_model.time_params.copy_(torch.tensor([[0.5, 0.3, 0.7, 0.45, 0.2, 0.95, 0.6, 0.5]]))
+    target_ts = torch.tensor([1.0, 2.0, 4.0, 5.0])
+    target_w2cs = sc.w2c.repeat(4, 1, 1).clone()
+    target_w2cs[:, 0, 3] = torch.tensor([0.05, -0.05, 0.1, -0.1])
+    out = model.render(t_frame, sc.w2c, sc.K, (W, H), target_ts=target_ts, target_w2cs=target_w2cs, return_depth=True,
+                       return_mask=True, mode="blury", stage="second")
+    N = len(stashes)
+    assert N == 11 and len(model._current_xys) == 11 and out["exposure_imgs"].shape == (11, 1, H, W, 17)
+    edge_any = np.zeros((1, H, W), bool)
+    for st in stashes:
+        edge_any |= st["meta"]["edge"] != 0
+    ok = torch.from_numpy(~edge_any)
+    # a scalar loss over what the trainer uses; no cotangent on knife-edge pixels, nor on the max (mask) / min (depth)
+    # channels (their arg-extremum may legitimately differ between two fp32 evaluations)
+    g = torch.Generator().manual_seed(5)
+    keys = ["img", "tracks_3d", "acc"]
+    wts = {k: torch.randn(out[k].shape, generator=g) for k in keys}
+    loss = 0
+    for k in keys:
+        m = ok.reshape((1, H, W) + (1,) * (out[k].dim() - 3))
+        wts[k] = wts[k] * m
+        loss = loss + (out[k] * wts[k]).sum()
+    params = {"fg." + k: v for k, v in fg.params.items()}
+    params.update({"bg." + k: v for k, v in bg.params.items()})
+    params.update({"motion_bases." + k: v for k, v in mb.params.items()})
+    mm_params = dict(model.move_model.named_parameters())
+    grads = torch.autograd.grad(loss, list(params.values()) + list(mm_params.values()), allow_unused=True)
+    # the trainer's control-step loop (trainer.py:967-989) restated literally on the reference's side channel
+    G = sc.G
+    stats = {"xys_grad_norm_acc": torch.zeros(G), "vis_count": torch.zeros(G, dtype=torch.int64),
+             "max_radii": torch.zeros(G)}
+    xys_grads = [st["means2d_grad"] for st in stashes]
+    batch_size = 1
+    for ii in range(len(model._current_xys)):
+        _current_radii, _current_img_wh = model._current_radii, model._current_img_wh
+        sel = _current_radii[ii] > 0
+        gidcs = torch.where(sel)[1]
+        xys_grad = xys_grads[ii].clone()
+        xys_grad[..., 0] *= _current_img_wh[0] / 2.0 * batch_size * len(model._current_xys)
+        xys_grad[..., 1] *= _current_img_wh[1] / 2.0 * batch_size * len(model._current_xys)
+        stats["xys_grad_norm_acc"].index_add_(0, gidcs, xys_grad[sel].norm(dim=-1))
+        stats["vis_count"].index_add_(0, gidcs, torch.ones_like(gidcs, dtype=torch.int64))
+    save = {"width": W, "height": H, "t": t_frame, "target_ts": target_ts.numpy(), "target_w2cs": target_w2cs.numpy(),
+            "w2c": sc.w2c.numpy(), "K": sc.K.numpy(), "ok": ok.numpy()}
+    for k, v in sc.tensors().items():
+        save["scene_" + k] = v.numpy()
+    for k, v in model.move_model.state_dict().items():
+        save["mm_" + k] = v.numpy()
+    for k in ["img", "mask", "tracks_3d", "depth", "acc", "deltaT", "RTs", "pred_sharp_img"]:
+        save["out_" + k] = out[k].detach().numpy()
+    save["out_exposure_first"] = out["exposure_imgs"][0].detach().numpy()
+    save["out_exposure_last"] = out["exposure_imgs"][-1].detach().numpy()
+    save["radii"] = torch.stack(model._current_radii).numpy()                # [11,1,G]
+    save["means2d_grad"] = torch.stack(xys_grads).numpy().astype(np.float32)  # [11,1,G,2]
+    for k in keys:
+        save["w_" + k] = wts[k].numpy()
+    for (k, _), gr in zip(list(params.items()) + [("mm." + k, v) for k, v in mm_params.items()], grads):
+        if gr is not None:
+            save["grad_" + k] = gr.numpy()
+    save["stat_xys_grad_norm_acc"] = stats["xys_grad_norm_acc"].numpy()
+    save["stat_vis_count"] = stats["vis_count"].numpy()
+    np.savez_compressed(os.path.join(HERE, "scene_render.npz"), **save)
+    print("wrote scene_render.npz", {k: tuple(v.shape) for k, v in save.items() if k.startswith("out_")},
+          "edge px", int(edge_any.sum()), "visible", int((save["radii"] > 0).sum()))
+
+
 def checkpoint_golden():
     """A checkpoint in the reference's own on-disk layout (trainer.py:126-140): the state dicts come from
     the reference's GaussianParams / MotionBases modules, nested exactly as SceneModel registers them
@@ -192,6 +350,7 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     camera_golden()
     checkpoint_golden()
+    scene_render_golden()
     deform_golden("k6_n5", G=600, K=6, N=5, seed=11)
     deform_golden("k10_n9", G=900, K=10, N=9, seed=12)
     deform_golden("k3_n1_int", G=257, K=3, N=1, seed=13, int_ts=True)

@@ -771,7 +771,9 @@ def test_frame_renderer_matches_reference_style_loop(mode):
         # the fused path applies the camera delta inside the deformation kernel (FMA order differs from the
         # torch matmul of the loop): agreement to fp32 round-off, held to the 1e-4 parity tolerance
         assert rel_err(out[k].detach().cpu().numpy(), ref[k].detach().cpu().numpy()) <= 1e-4, k
-    assert fr._current_radii.shape[0] == (11 if mode == "blury" else 1)
+    n_sub = 11 if mode == "blury" else 1
+    assert len(fr._current_radii) == len(fr._current_xys) == n_sub and fr._fused_radii.shape[0] == n_sub
+    assert fr._current_radii[0].shape == (1, fr.num_gaussians)
     # gradients of a scalar loss over every output the trainer uses
     g = torch.Generator().manual_seed(5)
     wts = {k: torch.randn(ref[k].shape, generator=g).to(DEV) for k in ["img", "mask", "tracks_3d", "depth", "acc", "exposure_imgs"]}
@@ -791,3 +793,168 @@ def test_frame_renderer_matches_reference_style_loop(mode):
         assert (a is None) == (b is None)
         if a is not None:
             assert scale_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-4, p.shape
+
+
+def _trainer_control_loop(stats, _current_xys, _current_radii, _current_img_wh, batch_size=1):
+    """Trainer._prepare_control_step's loop, flow3d/trainer.py:967-989, restated literally."""
+    assert len(_current_xys) == len(_current_radii)
+    for ii in range(0, len(_current_xys)):
+        sel = _current_radii[ii] > 0
+        gidcs = torch.where(sel)[1]
+        xys_grad = _current_xys[ii].grad.clone()
+        xys_grad[..., 0] *= _current_img_wh[0] / 2.0 * batch_size * len(_current_xys)
+        xys_grad[..., 1] *= _current_img_wh[1] / 2.0 * batch_size * len(_current_xys)
+        stats["xys_grad_norm_acc"].index_add_(0, gidcs, xys_grad[sel].norm(dim=-1))
+        stats["vis_count"].index_add_(0, gidcs, torch.ones_like(gidcs, dtype=torch.int64))
+        max_radii = torch.maximum(stats["max_radii"].index_select(0, gidcs), _current_radii[ii][sel] / max(_current_img_wh))
+        stats["max_radii"].index_put((gidcs,), max_radii)
+
+
+def test_frame_renderer_vs_reference_scene_model_render():
+    """tests/golden/scene_render.npz holds outputs, parameter gradients, the densifier side channel and the
+    control-step statistics of the reference's REAL SceneModel.render + MoveModel code (run on the CPU over a
+    gsplat stand-in backed by the oracle: tests/golden/make_golden.py::scene_render_golden).  FrameRenderer.render --
+    the fused N-sub-exposure path that is benchmarked -- must reproduce all of it, and the trainer's own control-step
+    loop (trainer.py:967-989, literal) must run on its side channel and agree with accumulate_densify_stats."""
+    from deblur4dgs_b200.control import accumulate_densify_stats
+    from deblur4dgs_b200.frame_renderer import CameraMotionModel, FrameRenderer
+    g = golden("scene_render.npz")
+    W, H, t = int(g["width"]), int(g["height"]), int(g["t"])
+    sc = {k[6:]: torch.from_numpy(np.asarray(v)).to(DEV) for k, v in g.items() if k.startswith("scene_")}
+    mm = CameraMotionModel()
+    mm.load_state_dict({k[3:]: torch.from_numpy(np.asarray(v)) for k, v in g.items() if k.startswith("mm_")})
+    fg = {k: sc["motion_coefs" if k == "motion_coefs" else "fg_" + k] for k in ["means", "quats", "scales", "colors", "opacities", "motion_coefs"]}
+    bg = {k: sc["bg_" + k] for k in ["means", "quats", "scales", "colors", "opacities"]}
+    w2c, K = T(g["w2c"]), T(g["K"])
+    fr = FrameRenderer(K, w2c, fg, sc["rots"], sc["transls"], bg, mm).to(DEV)
+    out = fr.render(t, w2c, K, (W, H), target_ts=T(g["target_ts"]), target_w2cs=T(g["target_w2cs"]), return_depth=True,
+                    return_mask=True, mode="blury", stage="second")
+    ok = g["ok"][0]
+    errs = {}
+    for k in ["img", "mask", "tracks_3d", "depth", "acc", "pred_sharp_img"]:
+        a, b = out[k].detach().cpu().numpy()[0][ok], g["out_" + k][0][ok]
+        errs[k] = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+    errs["exposure_first"] = rel_err(out["exposure_imgs"][0, 0].detach().cpu().numpy()[ok], g["out_exposure_first"][0][ok])
+    errs["exposure_last"] = rel_err(out["exposure_imgs"][-1, 0].detach().cpu().numpy()[ok], g["out_exposure_last"][0][ok])
+    errs["RTs"] = rel_err(out["RTs"].detach().cpu().numpy(), g["out_RTs"])
+    errs["deltaT"] = rel_err(out["deltaT"].detach().cpu().numpy(), g["out_deltaT"])
+    assert out["exposure_imgs"].shape == (11, 1, H, W, 17)
+    # radii of every sub-exposure: integers, exact
+    radii = torch.stack([r for r in fr._current_radii]).cpu().numpy()
+    assert radii.shape == g["radii"].shape
+    n_radii_diff = int((radii != g["radii"]).sum())
+    # gradients of the fixture's loss
+    loss = sum((out[k] * T(g["w_" + k])).sum() for k in ["img", "tracks_3d", "acc"])
+    loss.backward()
+    named = {"fg." + k: v for k, v in fr.fg.items()}
+    named.update({"bg." + k: v for k, v in fr.bg.items()})
+    named.update({"motion_bases.rots": fr.rots, "motion_bases.transls": fr.transls})
+    named.update({"mm." + k: v for k, v in fr.move_model.named_parameters()})
+    gerr = {}
+    for k, p in named.items():
+        if "grad_" + k in g:
+            assert p.grad is not None, k
+            gerr[k] = scale_err(p.grad.cpu().numpy(), g["grad_" + k])
+    xg = torch.stack([x.grad for x in fr._current_xys]).cpu().numpy()
+    gerr["means2d"] = scale_err(xg, g["means2d_grad"])
+    # the reference trainer's control-step loop on the side channel, vs the fixture and vs the fused kernel
+    G = fr.num_gaussians
+    mk = lambda: {"xys_grad_norm_acc": torch.zeros(G, device=DEV), "vis_count": torch.zeros(G, dtype=torch.int64, device=DEV),
+                  "max_radii": torch.zeros(G, device=DEV)}
+    st_loop, st_kernel = mk(), mk()
+    _trainer_control_loop(st_loop, fr._current_xys, fr._current_radii, fr._current_img_wh)
+    accumulate_densify_stats(st_kernel, fr._fused_xys.grad, fr._fused_radii, (W, H), batch_size=1)
+    e_stat = scale_err(st_loop["xys_grad_norm_acc"].cpu().numpy(), g["stat_xys_grad_norm_acc"])
+    report(test="scene_render_fixture", kind="frame", radii_differ=n_radii_diff, stat_err=e_stat, **errs,
+           **{"grad_" + k: v for k, v in gerr.items()})
+    assert n_radii_diff == 0
+    for k, v in errs.items():
+        assert v <= 1e-4, (k, v)
+    for k, v in gerr.items():
+        assert v <= 2e-4, (k, v)
+    assert np.array_equal(st_loop["vis_count"].cpu().numpy(), g["stat_vis_count"])
+    assert e_stat <= 2e-4
+    assert torch.equal(st_kernel["vis_count"], st_loop["vis_count"])
+    assert torch.allclose(st_kernel["xys_grad_norm_acc"], st_loop["xys_grad_norm_acc"], rtol=1e-5, atol=1e-9)
+    assert torch.equal(st_kernel["max_radii"], st_loop["max_radii"])
+
+
+def test_checkpoint_replay_through_render_path():
+    """Row f2: tests/golden/ckpt_small.pt (written with the reference's own GaussianParams / MotionBases modules in the
+    layout Trainer.save_checkpoint uses) loaded by checkpoint.load_checkpoint and replayed through the fused render path
+    on the GPU, against the oracle run on the oracle-deformed scene."""
+    from deblur4dgs_b200.checkpoint import load_checkpoint
+    from deblur4dgs_b200.scene import render_subexposures
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ckpt_small.pt")
+    sc, extras = load_checkpoint(path, 96, 64, frame=2, N=3)
+    assert extras["global_step"] == 1234 and extras["epoch"] == 7
+    s = sc.to(DEV)
+    scales, opac, colors = s.scales_all(), s.opacities_all(), s.colors_all(4)
+    bg = torch.full((1, 4), 0.25, device=DEV)
+    out = render_subexposures(s.fg_means, s.fg_quats, s.motion_coefs, s.bg_means, s.bg_quats, s.rots, s.transls, s.times,
+                              s.RTs, scales, opac, colors, s.w2c, s.K, 96, 64, backgrounds=bg, render_mode="RGB+ED")
+    M, Q = odef.deform_subexposures(sc.fg_means, sc.fg_quats, sc.motion_coefs, sc.bg_means, sc.bg_quats, sc.rots,
+                                    sc.transls, sc.times, sc.RTs)
+    for i in range(3):
+        rc, ra, meta = orc.rasterization(M[i].numpy(), Q[i].numpy(), scales.cpu().numpy(), opac.cpu().numpy(),
+                                         colors.cpu().numpy(), sc.w2c.numpy(), sc.K.numpy(), 96, 64,
+                                         backgrounds=bg.cpu().numpy(), render_mode="RGB+ED")
+        ok = meta["edge"][0] == 0
+        assert np.array_equal(out["radii"][i].cpu().numpy(), meta["radii"][0])
+        e = rel_err(out["exposure_imgs"][i, 0].cpu().numpy()[ok], rc[0][ok])
+        report(test="ckpt_replay", kind="ckpt", subexposure=i, rel_err=e, n_isects=int(meta["isect_ids"].shape[0]))
+        assert e <= 1e-4
+
+
+def test_capacity_mode_equals_sync_mode_and_flags_overflow():
+    """rendering.RenderCapacity: the sync-free binning (capacity-sized buffers, device-side count, overflow flag) must
+    give bit-identical renders and gradients to the synchronising mode, and an undersized capacity must be reported."""
+    from deblur4dgs_b200._cabi import D4Error
+    from deblur4dgs_b200.rendering import RenderCapacity, rasterization
+    sc = make_scene(G=20000, width=320, height=192, K=4, N=1, seed=3, scale_mult=1.5)
+    inp = scene_inputs(sc, 16, C=2)
+    names = ["means", "quats", "scales", "opacities", "colors", "viewmats", "backgrounds"]
+
+    def run(capacity):
+        t = {k: T(inp[k], True) for k in names}
+        rc, ra, meta = rasterization(means=t["means"], quats=t["quats"], scales=t["scales"], opacities=t["opacities"],
+                                     colors=t["colors"], backgrounds=t["backgrounds"], viewmats=t["viewmats"],
+                                     Ks=T(inp["Ks"]), width=320, height=192, packed=False, render_mode="RGB+ED",
+                                     capacity=capacity)
+        (rc.sum() + (ra * ra).sum()).backward()
+        return rc.detach(), ra.detach(), meta, {k: t[k].grad for k in names}
+
+    rc0, ra0, meta0, g0 = run(None)
+    n = meta0["isect_ids"].numel()
+    cap = RenderCapacity()
+    run(cap)  # learns (synchronises once)
+    assert cap.ready and cap.n_isects >= n and cap.seen_isects == n
+    rc1, ra1, meta1, g1 = run(cap)  # sync-free
+    assert meta1["isect_ids"].numel() == cap.n_isects  # capacity-sized buffers
+    torch.cuda.synchronize()
+    cap.check()
+    assert cap.last_n_isects == n
+    assert torch.equal(rc0, rc1) and torch.equal(ra0, ra1)
+    assert torch.equal(meta0["isect_ids"], meta1["isect_ids"][:n]) and torch.equal(meta0["flatten_ids"], meta1["flatten_ids"][:n])
+    assert torch.equal(meta0["isect_offsets"], meta1["isect_offsets"])
+    for k in names:
+        # atomics: the summation order of the per-Gaussian gradient sums is not fixed
+        assert scale_err(g1[k].cpu().numpy(), g0[k].cpu().numpy()) <= 1e-5, k
+    # undersized buffers: the render completes (tiles beyond the capacity are dropped), the flag comes back
+    small = RenderCapacity()
+    small.n_isects, small.sort_cap = n // 2, cap.sort_cap
+    run(small)
+    torch.cuda.synchronize()
+    with pytest.raises(D4Error):
+        small.check()
+    assert small.n_isects >= n  # the capacity has been raised: the next render fits
+    run(small)
+    torch.cuda.synchronize()
+    small.check()
+    # undersized per-tile sort
+    tiny = RenderCapacity()
+    tiny.n_isects, tiny.sort_cap = cap.n_isects, 8
+    run(tiny)
+    torch.cuda.synchronize()
+    with pytest.raises(D4Error):
+        tiny.check()
