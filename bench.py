@@ -197,7 +197,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c5"])
-    ap.add_argument("--shard", default="frames", choices=["frames", "subexposures"])
+    ap.add_argument("--shard", default="frames", choices=["frames", "subexposures", "bands"],
+                    help="frames: one blurry frame per rank (weak scaling, the headline); bands: ONE frame's "
+                         "(sub-exposure, tile-row band) units over the ranks (strong scaling, BASELINE configs[3]; also "
+                         "measured as the 'strong' object of every multi-GPU frames run); subexposures: round-robin "
+                         "sub-exposures (strong, unbalanced for N=9 on 8 ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync", action="store_true", help="gsplat-style binning with its device->host read-back every step "
                                                         "(default: sync-free capacity mode, rendering.RenderCapacity)")
@@ -214,7 +218,8 @@ def main():
 
     import torch.distributed as dist
     from deblur4dgs_b200 import _cabi
-    from deblur4dgs_b200.parallel import allreduce_sum_, render_frame_sharded, shard_indices
+    from deblur4dgs_b200 import parallel
+    from deblur4dgs_b200.parallel import allreduce_sum_, render_frame_banded, render_frame_sharded, shard_indices
     from deblur4dgs_b200.rendering import RenderCapacity
     from deblur4dgs_b200.scene import assemble_gaussians, render_subexposures
     from deblur4dgs_b200.synthetic import CONFIGS, make_config
@@ -255,9 +260,11 @@ def main():
     # sync-free tile binning: buffers sized by a learnt capacity, the intersection count never leaves the device inside
     # a step (the first warm-up step synchronises once to learn the sizes; overflow is checked after the timed regions)
     cap = None if args.sync else RenderCapacity()
+    cap_bands = None if args.sync else RenderCapacity()
 
-    def step(scn, want_outputs=False):
+    def step(scn, want_outputs=False, shard=None):
         """One blurry frame forward + backward from the raw scene parameters."""
+        shard = shard or args.shard
         p = {k: getattr(scn, k).detach().requires_grad_(True) for k in param_names}
         # activations + fg|bg concat + [rgb | fg mask | track channels] feature vector (row f1), one kernel
         scales, opac, colors = assemble_gaussians(p["fg_scales"], p["bg_scales"], p["fg_opacities"], p["bg_opacities"],
@@ -265,13 +272,18 @@ def main():
                                                   extra=scn.extra_channels if scn.extra_channels.shape[1] else None,
                                                   with_mask=True)
 
-        def local(times, RTs, combine):
+        def local(times, RTs, combine, row_windows=None):
             return render_subexposures(p["fg_means"], p["fg_quats"], p["motion_coefs"], p["bg_means"], p["bg_quats"],
                                        p["rots"], p["transls"], times, RTs, scales, opac, colors, scn.w2c, scn.K, W, H,
                                        backgrounds=bg, render_mode="RGB+ED", combine=combine, ref_quirk=True,
-                                       capacity=cap)
+                                       capacity=cap if row_windows is None else cap_bands, row_windows=row_windows)
 
-        if world > 1 and args.shard == "subexposures":
+        if world > 1 and shard == "bands":
+            def render_units(t, r, row0, band_h):
+                o = local(t, r, False, (row0, band_h))
+                return o["exposure_imgs"], o["exposure_alphas"]
+            img, acc = render_frame_banded(scn.times, scn.RTs, H, render_units, ref_quirk=True)
+        elif world > 1 and shard == "subexposures":
             def render_local(t, r):
                 o = local(t, r, False)
                 if cap is None:
@@ -289,7 +301,12 @@ def main():
             allreduce_sum_(grads)
         return (img, acc, grads) if want_outputs else None
 
-    frames_per_step_local = N if (world == 1 or args.shard == "frames") else len(shard_indices(N, rank, world))
+    if world == 1 or args.shard == "frames":
+        frames_per_step_local = N
+    elif args.shard == "bands":
+        frames_per_step_local = N / world  # N (sub-exposure, band) units = N / world whole sub-exposure frames
+    else:
+        frames_per_step_local = len(shard_indices(N, rank, world))
     frames_per_step_global = N * world if args.shard == "frames" else N
 
     for _ in range(args.warmup):
@@ -353,9 +370,42 @@ def main():
         cap.check()
         graph_ms = g0.elapsed_time(g1) / args.steps
     n_sort_passes = math.ceil((32 + _cabi.lib().d4_tile_n_bits(math.ceil(W / 16) * math.ceil(H / 16)) +
-                               int(math.floor(math.log2(frames_per_step_local))) + 1) / 8)
+                               int(math.floor(math.log2(max(1, int(frames_per_step_local))))) + 1) / 8)
     if "d4_sort_pairs_u64" in prof:  # radix fallback only: 3 kernels per pass (the default bucketed binning has none)
         launches_per_step += (3 * n_sort_passes - 1) * len(prof["d4_sort_pairs_u64"]) / args.steps
+
+    # ---- timed region 1c (multi-GPU frames runs): STRONG scaling of ONE blurry frame -- BASELINE configs[3] --------
+    # the frame's N x world (sub-exposure, tile-row band) units over the ranks, image / extrema / gradient all-reduce
+    strong = None
+    if world > 1 and args.shard == "frames":
+        sc_frame = make_config(args.config, seed=seed).to(dev) if not args.checkpoint else sc  # the SAME frame on every rank
+        for _ in range(max(3, args.warmup)):
+            step(sc_frame, shard="bands")
+        torch.cuda.synchronize()
+        cprof = {}
+        parallel.PROFILE = cprof
+        dist.barrier()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            step(sc_frame, shard="bands")
+        s1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        parallel.PROFILE = None
+        if cap_bands is not None:
+            cap_bands.check()
+        coll = sum(a.elapsed_time(b) for v in cprof.values() for a, b in v) / args.steps
+        t = torch.tensor([s0.elapsed_time(s1), coll], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong_ms = float(t[0].item()) / args.steps
+        strong = {"partition": f"{N} sub-exposures x {world} tile-row bands, {N} units per rank", "frames_per_s": N / (strong_ms * 1e-3),
+                  "ms_per_blurry_frame": strong_ms, "speedup_vs_1gpu": (ms_total / args.steps) / strong_ms,
+                  "collective_ms": float(t[1].item()),
+                  "collectives": {k: len(v) / args.steps for k, v in cprof.items()},
+                  "note": "speedup against this run's own one-frame-per-GPU step (ms_per_step, which includes the gradient "
+                          "all-reduce); collective_ms = CUDA-event time inside the NCCL calls (max over ranks)"}
 
     # ---- timed region 2: end to end through the public API with HOST buffers --------------
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
@@ -491,6 +541,7 @@ def main():
             "gpu_launches_detail": {"libd4gs_kernels_per_step": own_launches_per_step,
                                     "torch_zero_fills_per_step": fills_per_step,
                                     "host_syncs_per_step": 1 if cap is None else 0},
+            "strong": strong,
             "graph": None if graph_ms is None else {"ms_per_step": graph_ms, "value": frames_per_step_global / (graph_ms * 1e-3),
                                                     "note": "the same step (fwd+bwd) replayed from one captured CUDA graph"},
             "clocks": clocks,

@@ -22,7 +22,7 @@ I, L, F = c_int, c_int64, c_float
 PROTOTYPES = {
     "d4_version": (c_int, []),
     "d4_last_error": (c_char_p, []),
-    "d4_project_fwd": (c_int, [P, L, P, L, P, P, L, P, L, I, I, I, I, F, F, F, F, I, I, I, P, P, P, P, P, P]),
+    "d4_project_fwd": (c_int, [P, L, P, L, P, P, L, P, L, I, I, I, I, F, F, F, F, I, I, I, P, P, P, P, P, P, I, P]),
     "d4_project_bwd": (c_int, [P, L, P, L, P, P, L, P, L, I, I, I, I, F, P, P, P, P, P, P, P, P, P, P]),
     "d4_scan_workspace_bytes": (c_size_t, [L]),
     "d4_exclusive_scan_i32": (c_int, [P, L, P, P, P, c_size_t, P]),

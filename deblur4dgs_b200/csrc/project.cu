@@ -20,7 +20,7 @@ project_fwd_kernel(const float *__restrict__ means, int64_t means_cs, const floa
                    float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h,
                    int32_t *__restrict__ radii, float *__restrict__ means2d,
                    float *__restrict__ depths, float *__restrict__ conics,
-                   int32_t *__restrict__ tiles_per_gauss) {
+                   int32_t *__restrict__ tiles_per_gauss, const int32_t *__restrict__ cam_row0, int window_height) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)C * G) return;
     int c = (int)(idx / G);
@@ -39,6 +39,14 @@ project_fwd_kernel(const float *__restrict__ means, int64_t means_cs, const floa
     const float *sp = scales + 3LL * g;
     float s[3] = {__ldg(sp), __ldg(sp + 1), __ldg(sp + 2)};
     ProjOut o = project_one(m, q, s, Vl, Kl, width, height, eps2d, near_plane, far_plane, radius_clip);
+    if (cam_row0) {
+        // row window of this camera (multi-GPU tile-row bands): the projection itself is that of the FULL image
+        // (same tan-fov clamp, same visibility); the window only moves the origin of the rows -- an exact fp32
+        // subtraction of a small integer -- and drops what cannot touch its rows
+        o.m2y = __fsub_rn(o.m2y, (float)cam_row0[c]);
+        const float r = (float)o.radius;
+        if (o.radius > 0 && (__fadd_rn(o.m2y, r) <= 0.f || __fsub_rn(o.m2y, r) >= (float)window_height)) o.radius = 0;
+    }
     radii[idx] = o.radius;
     reinterpret_cast<float2 *>(means2d)[idx] = make_float2(o.m2x, o.m2y);
     depths[idx] = o.depth;
@@ -191,8 +199,11 @@ extern "C" int d4_project_fwd(const float *means, int64_t means_cam_stride, cons
                               int G, int width, int height, float eps2d, float near_plane,
                               float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h,
                               int32_t *radii, float *means2d, float *depths, float *conics,
-                              int32_t *tiles_per_gauss, d4_stream_t stream) {
+                              int32_t *tiles_per_gauss, const int32_t *cam_row0, int window_height,
+                              d4_stream_t stream) {
     D4_CHECK_ARG(C >= 1 && G >= 0 && width > 0 && height > 0 && tile_size > 0, "d4_project_fwd: bad sizes");
+    D4_CHECK_ARG(!cam_row0 || (window_height > 0 && tile_h == (window_height + tile_size - 1) / tile_size),
+                 "d4_project_fwd: a row window needs window_height > 0 and tile_h of the window");
     if (G == 0) return 0;
     D4_CHECK_ARG(means && quats && scales && viewmats && Ks && radii && means2d && depths && conics,
                  "d4_project_fwd: null pointer");
@@ -203,7 +214,7 @@ extern "C" int d4_project_fwd(const float *means, int64_t means_cam_stride, cons
     project_fwd_kernel<<<cdiv(n, kProjThreads), kProjThreads, 0, as_stream(stream)>>>(
         means, means_cam_stride, quats, quats_cam_stride, scales, viewmats, viewmat_cam_stride, Ks,
         k_cam_stride, C, G, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size, tile_w,
-        tile_h, radii, means2d, depths, conics, tiles_per_gauss);
+        tile_h, radii, means2d, depths, conics, tiles_per_gauss, cam_row0, window_height);
     D4_CHECK_LAUNCH("d4_project_fwd");
     return 0;
 }

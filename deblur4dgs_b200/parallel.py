@@ -14,6 +14,16 @@ The path shards two ways, both with replicated parameters (~20 MB at config c3):
   N-way combine of scene_model.py:386-397 distributed; backward exchange: SUM all-reduce
   of the parameter gradients.
 
+* ``"bands"`` (strong scaling, balanced for any N: the 2-D partition of SURVEY 8e): every sub-exposure is
+  cut into R tile-row bands, the N x R (sub-exposure, band) units are dealt N to a rank in sub-exposure-major
+  order, and a rank renders its N units as one "C = N cameras" launch with per-camera row windows
+  (``rendering.rasterization(row_windows=...)``: full-image projection, binning / blend on the band only).
+  Forward exchange: one SUM all-reduce of the pre-scaled partial image (+ alpha plane), one MAX all-reduce of the
+  (mask, -depth) extrema and one MIN all-reduce of the winning sub-exposure index (so that ties -- the mask
+  channel is exactly 0 or 1 over large areas -- route their gradient once, to the first sub-exposure, as
+  torch.max / min do); backward exchange: the SUM all-reduce of the parameter gradients.  Reproduces the
+  reference's in-place alias quirk (``ref_quirk``), i.e. it is training-equivalent to the single-GPU path.
+
 Everything here is host logic over ``torch.distributed``; the kernels are unchanged.
 """
 from __future__ import annotations
@@ -23,6 +33,21 @@ from typing import Dict, Iterable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 from torch import Tensor
+
+
+PROFILE = None  # bench.py sets this to a dict: tag -> [(start, end) CUDA events] around every collective
+
+
+def _all_reduce(t: Tensor, op, group, tag: str):
+    prof = PROFILE
+    if prof is not None and t.is_cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(t, op=op, group=group)
+        e1.record()
+        prof.setdefault(tag, []).append((e0, e1))
+    else:
+        dist.all_reduce(t, op=op, group=group)
 
 
 def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
@@ -48,7 +73,7 @@ def allreduce_sum_(tensors: Iterable[Optional[Tensor]], group=None, bucket_bytes
         if not bucket:
             return
         flat = torch.cat([t.reshape(-1) for t in bucket])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(flat, dist.ReduceOp.SUM, group, "grad_sum")
         off = 0
         for t in bucket:
             n = t.numel()
@@ -127,3 +152,124 @@ def render_frame_sharded(scene_args: Dict, times: Tensor, RTs: Optional[Tensor],
         from .scene import combine_subexposures
         return combine_subexposures(imgs, alphas, 3 if D > 3 else -1, 16 if D > 16 else -1, ref_quirk=False)
     return _DistCombine.apply(imgs, alphas, N, 3 if D > 3 else -1, 16 if D > 16 else -1, group)
+
+
+# ------------------------------------------------------------------------------------------------ #
+# 2-D partition: (sub-exposure, tile-row band) units
+# ------------------------------------------------------------------------------------------------ #
+def band_layout(height: int, world: int, tile_size: int = 16):
+    """R = world bands of equal height (a multiple of the tile size) that cover the image: (band_rows_px, n_bands)."""
+    tile_h = (height + tile_size - 1) // tile_size
+    rows = (tile_h + world - 1) // world
+    return rows * tile_size, world
+
+
+def band_units(n_sub: int, rank: int, world: int) -> List[tuple]:
+    """The (sub-exposure, band) units of ``rank``: N x R units in sub-exposure-major order, N consecutive ones each."""
+    units = [(s, b) for s in range(n_sub) for b in range(world)]
+    return units[rank * n_sub:(rank + 1) * n_sub]
+
+
+class _BandCombine(torch.autograd.Function):
+    """N-way combine (scene_model.py:386-397) over units spread across ranks.  imgs [U,1,band_h,W,D], alphas
+    [U,1,band_h,W,1] are this rank's units, ``subs`` / ``bands`` their coordinates."""
+
+    @staticmethod
+    def forward(ctx, imgs, alphas, subs, bands, n_sub, n_bands, height, max_ch, min_ch, ref_quirk, group):
+        U, _, bh, W, D = imgs.shape
+        dev, dt = imgs.device, imgs.dtype
+        Hp = n_bands * bh
+        n_ext = n_sub - 1 if ref_quirk else n_sub  # extrema over r_0 .. r_{N-2} (+ the mean) in quirk mode
+        part = torch.zeros((Hp, W, D + 1), dtype=dt, device=dev)
+        chans = [c for c in (max_ch, min_ch) if 0 <= c < D]
+        sign = {max_ch: 1.0, min_ch: -1.0}
+        ext = torch.full((Hp, W, max(len(chans), 1)), float("-inf"), dtype=dt, device=dev)
+        for u in range(U):
+            rows = slice(bands[u] * bh, (bands[u] + 1) * bh)
+            part[rows, :, :D] += imgs[u, 0] / n_sub
+            part[rows, :, D:] += alphas[u, 0] / n_sub
+            if subs[u] < n_ext:
+                for j, ch in enumerate(chans):
+                    ext[rows, :, j] = torch.maximum(ext[rows, :, j], sign[ch] * imgs[u, 0, :, :, ch])
+        distributed = dist.is_initialized() and dist.get_world_size(group) > 1
+        if distributed:
+            _all_reduce(part, dist.ReduceOp.SUM, group, "image_sum")
+            if chans:
+                _all_reduce(ext, dist.ReduceOp.MAX, group, "extrema_max")
+        # first sub-exposure attaining the extremum (torch.max / min(dim) semantics), agreed on globally
+        big = 2 ** 30
+        winner = torch.full(ext.shape, big, dtype=torch.int32, device=dev)
+        for u in range(U):
+            if subs[u] < n_ext:
+                rows = slice(bands[u] * bh, (bands[u] + 1) * bh)
+                for j, ch in enumerate(chans):
+                    hit = (sign[ch] * imgs[u, 0, :, :, ch]) == ext[rows, :, j]
+                    winner[rows, :, j] = torch.where(hit, torch.clamp(winner[rows, :, j], max=subs[u]), winner[rows, :, j])
+        if distributed and chans:
+            _all_reduce(winner, dist.ReduceOp.MIN, group, "winner_min")
+        out = part[:height, :, :D].clone()
+        out_alpha = part[:height, :, D:].clone()
+        for j, ch in enumerate(chans):
+            best = sign[ch] * ext[:height, :, j]
+            mean = out[:, :, ch]
+            if ref_quirk:
+                mean_wins = (mean > best) if ch == max_ch else (mean < best)
+                if n_ext == 0:
+                    mean_wins = torch.ones_like(mean_wins)
+                winner[:height, :, j] = torch.where(mean_wins, torch.full_like(winner[:height, :, j], -1), winner[:height, :, j])
+                out[:, :, ch] = torch.where(mean_wins, mean, best)
+            else:
+                out[:, :, ch] = best
+        ctx.save_for_backward(winner)
+        ctx.cfg = (subs, bands, n_sub, bh, height, chans, imgs.shape, alphas.shape)
+        return out[None], out_alpha[None]
+
+    @staticmethod
+    def backward(ctx, v_out, v_alpha):
+        (winner,) = ctx.saved_tensors
+        subs, bands, n_sub, bh, height, chans, ishape, ashape = ctx.cfg
+        U, _, _, W, D = ishape
+        dev = winner.device
+        Hp = winner.shape[0]
+        vo = torch.zeros((Hp, W, D), dtype=torch.float32, device=dev)
+        va = torch.zeros((Hp, W, 1), dtype=torch.float32, device=dev)
+        if v_out is not None:
+            vo[:height] = v_out[0]
+        if v_alpha is not None:
+            va[:height] = v_alpha[0]
+        v_imgs = torch.empty(ishape, dtype=torch.float32, device=dev)
+        v_alphas = torch.empty(ashape, dtype=torch.float32, device=dev)
+        for u in range(U):
+            rows = slice(bands[u] * bh, (bands[u] + 1) * bh)
+            v_imgs[u, 0] = vo[rows] / n_sub
+            v_alphas[u, 0] = va[rows] / n_sub
+            for j, ch in enumerate(chans):
+                w = winner[rows, :, j]
+                routed = torch.where(w == subs[u], vo[rows, :, ch], torch.zeros_like(vo[rows, :, ch]))
+                v_imgs[u, 0, :, :, ch] = torch.where(w < 0, vo[rows, :, ch] / n_sub, routed)  # -1: the mean itself won
+        return v_imgs, v_alphas, None, None, None, None, None, None, None, None, None
+
+
+def combine_band_units(imgs: Tensor, alphas: Tensor, subs: Sequence[int], bands: Sequence[int], n_sub: int, n_bands: int,
+                       height: int, ref_quirk: bool = True, group=None):
+    D = imgs.shape[-1]
+    return _BandCombine.apply(imgs, alphas, list(subs), list(bands), int(n_sub), int(n_bands), int(height),
+                              3 if D > 3 else -1, 16 if D > 16 else -1, bool(ref_quirk), group)
+
+
+def render_frame_banded(times: Tensor, RTs: Optional[Tensor], height: int, render_units, ref_quirk: bool = True, group=None):
+    """Strong scaling, 2-D partition: this rank renders N (sub-exposure, row band) units of ONE frame.
+
+    ``render_units(times_u [U], RTs_u [U,3,4] | None, row0 i32 [U], band_h) -> (imgs [U,1,band_h,W,D], alphas
+    [U,1,band_h,W,1])`` is the single-GPU path with row windows (``scene.render_subexposures(..., row_windows=(row0,
+    band_h), combine=False)``).  Returns the combined image [1,H,W,D] and alpha [1,H,W,1], replicated on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    N = times.shape[0]
+    band_h, n_bands = band_layout(height, world)
+    units = band_units(N, rank, world)
+    subs, bands = [u[0] for u in units], [u[1] for u in units]
+    idx = torch.as_tensor(subs, dtype=torch.long, device=times.device)
+    row0 = torch.as_tensor([b * band_h for b in bands], dtype=torch.int32, device=times.device)
+    imgs, alphas = render_units(times[idx], None if RTs is None else RTs[idx], row0, band_h)
+    return combine_band_units(imgs, alphas, subs, bands, N, n_bands, height, ref_quirk, group)

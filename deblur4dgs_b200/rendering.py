@@ -56,14 +56,19 @@ class RenderCapacity:
 
     The first render through a fresh object runs in the ordinary synchronising mode to learn the sizes."""
 
+    RING = 16  # pinned result slots: one per binning in flight
+
     def __init__(self, headroom: float = 1.3):
         self.headroom = float(headroom)
         self.n_isects = 0   # capacity of the per-intersection buffers (0: not known yet)
         self.sort_cap = 0   # capacity of the per-tile shared-memory sort
         self.seen_isects = self.seen_tile = 0
         self.overflowed = False
-        self._host = None   # pinned int64 [3]: n_isects, max per tile, overflow flag
-        self._event = None
+        self._host = None   # pinned int64 [RING, 3]: n_isects, max per tile, overflow flag
+        self._pending = []  # (event | None, slot) in issue order
+        self._slot = 0
+        self._stream = None
+        self._last_n = 0
 
     @property
     def ready(self) -> bool:
@@ -78,46 +83,76 @@ class RenderCapacity:
         while sort_cap < want:
             sort_cap <<= 1
         self.sort_cap = max(self.sort_cap, min(sort_cap, cap_max))
+        self._last_n = n_isects
 
     def record(self, stats: Tensor):
-        """Enqueue the async copy of (n_isects, max per tile, overflow) to pinned memory."""
+        """Enqueue the async copy of (n_isects, max per tile, overflow) to pinned memory.  Outside graph capture the copy
+        runs on a side stream: on the compute stream it would queue behind whatever large device -> host download the
+        caller has in flight on the copy engine, and stall the kernels behind it."""
         if self._host is None:
-            self._host = torch.zeros(3, dtype=torch.int64).pin_memory()
-        self._host.copy_(stats[:3], non_blocking=True)
+            self._host = torch.zeros((self.RING, 3), dtype=torch.int64).pin_memory()
+        if len(self._pending) >= self.RING:
+            self._drain(block=True)
+        slot = self._slot
+        self._slot = (slot + 1) % self.RING
         if torch.cuda.is_current_stream_capturing():
-            self._event = None  # replayed with the graph: read with check() after a synchronize
-        else:
-            self._event = torch.cuda.Event()
-            self._event.record()
+            self._host[slot].copy_(stats[:3], non_blocking=True)  # replayed with the graph: read by check()
+            self._pending = [(None, slot)]
+            return
+        cur = torch.cuda.current_stream()
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=stats.device)
+        binned = torch.cuda.Event()
+        binned.record(cur)
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(binned)
+            self._host[slot].copy_(stats[:3], non_blocking=True)
+            stats.record_stream(self._stream)
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        self._pending.append((ev, slot))
 
-    def _consume(self):
-        n, mx, ovf = (int(x) for x in self._host.tolist())
+    def _consume(self, slot: int):
+        n, mx, ovf = (int(x) for x in self._host[slot].tolist())
         self.learn(n, mx)
         if ovf:
             self.overflowed = True
-            self._host[2] = 0
+            self._host[slot, 2] = 0
             raise _cabi.D4Error(f"tile binning overflowed its capacity in a previous render ({n} intersections, {mx} in one "
                                 f"tile; that render dropped the tiles beyond it) -- capacity raised to {self.n_isects} / "
                                 f"{self.sort_cap}, render again")
 
+    def _drain(self, block: bool):
+        while self._pending:
+            ev, slot = self._pending[0]
+            if ev is not None:
+                if block:
+                    ev.synchronize()
+                elif not ev.query():
+                    return
+            elif not block:
+                return  # recorded under graph capture: only check() (after a synchronize) may read it
+            self._pending.pop(0)
+            self._consume(slot)
+
     @property
     def last_n_isects(self) -> int:
         """Intersection count of the last binning that poll() / check() has looked at (or of the learning render)."""
-        return int(self._host[0]) if self._host is not None and int(self._host[0]) > 0 else self.seen_isects
+        return self._last_n
 
     def poll(self):
-        """Non-blocking: look at the last finished binning, if any."""
-        if torch.cuda.is_current_stream_capturing():
-            return
-        if self._event is not None and self._event.query():
-            self._event = None
-            self._consume()
+        """Non-blocking: look at the binnings that have finished, if any."""
+        if not torch.cuda.is_current_stream_capturing():
+            self._drain(block=False)
 
     def check(self):
-        """After a device synchronisation: validate the last binning (also under CUDA graph replay)."""
-        if self._host is not None:
-            self._event = None
-            self._consume()
+        """Blocking: validate every binning issued so far (call after a synchronize when replaying a CUDA graph)."""
+        pend = list(self._pending)
+        try:
+            self._drain(block=True)
+        finally:
+            if pend and pend[-1][0] is None:  # a captured graph keeps writing its slot on every replay
+                self._pending = [pend[-1]]
 
 
 def _check_cuda(*ts):
@@ -158,13 +193,16 @@ def _cam_layout(means: Tensor, quats: Tensor, viewmats: Tensor, Ks: Tensor, G: i
 class _Projection(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
-                tile_size):
-        _check_cuda(means, quats, scales, viewmats, Ks)
+                tile_size, row0=None, window_height=0):
+        _check_cuda(means, quats, scales, viewmats, Ks, row0)
         means, quats, scales, viewmats, Ks = map(_f32c, (means, quats, scales, viewmats, Ks))
         G = scales.shape[0]
         C, ms, qs, vs, ks = _cam_layout(means, quats, viewmats, Ks, G)
         dev = means.device
-        tile_w, tile_h = math.ceil(width / tile_size), math.ceil(height / tile_size)
+        tile_w, tile_h = math.ceil(width / tile_size), math.ceil((window_height or height) / tile_size)
+        if row0 is not None:
+            row0 = row0.to(torch.int32).contiguous()
+            assert row0.shape == (C,) and window_height > 0
         radii = torch.empty((C, G), dtype=torch.int32, device=dev)
         means2d = torch.empty((C, G, 2), dtype=torch.float32, device=dev)
         depths = torch.empty((C, G), dtype=torch.float32, device=dev)
@@ -172,7 +210,7 @@ class _Projection(torch.autograd.Function):
         tiles_per_gauss = torch.empty((C, G), dtype=torch.int32, device=dev)
         call("d4_project_fwd", ptr(means), ms, ptr(quats), qs, ptr(scales), ptr(viewmats), vs, ptr(Ks), ks, C, G,
              width, height, eps2d, near_plane, far_plane, radius_clip, tile_size, tile_w, tile_h, ptr(radii),
-             ptr(means2d), ptr(depths), ptr(conics), ptr(tiles_per_gauss), stream_ptr())
+             ptr(means2d), ptr(depths), ptr(conics), ptr(tiles_per_gauss), ptr(row0), int(window_height), stream_ptr())
         ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii, conics)
         ctx.cfg = (C, G, ms, qs, vs, ks, width, height, eps2d)
         ctx.mark_non_differentiable(radii, tiles_per_gauss)
@@ -206,15 +244,19 @@ class _Projection(torch.autograd.Function):
         v_viewmats = None
         if want_vm:
             v_viewmats = v_vm_full if viewmats.shape[0] == C else v_vm_full.sum(0, keepdim=True)
-        return (v_means, v_quats, v_scales, v_viewmats, None, None, None, None, None, None, None, None)
+        return (v_means, v_quats, v_scales, v_viewmats, None, None, None, None, None, None, None, None, None, None)
 
 
 def fully_fused_projection(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
-                           far_plane=1e10, radius_clip=0.0, tile_size=16):
+                           far_plane=1e10, radius_clip=0.0, tile_size=16, row_windows=None):
     """gsplat.fully_fused_projection (packed=False): returns (radii i32 [C,G], means2d [C,G,2],
-    depths [C,G], conics [C,G,3], tiles_per_gauss i32 [C,G])."""
+    depths [C,G], conics [C,G,3], tiles_per_gauss i32 [C,G]).
+
+    row_windows = (row0 i32 [C], window_height): camera c covers rows [row0[c], row0[c] + window_height) of the
+    image only (multi-GPU tile-row bands); means2d.y comes back relative to the window."""
+    row0, wh = (None, 0) if row_windows is None else row_windows
     return _Projection.apply(means, quats, scales, viewmats, Ks, int(width), int(height), float(eps2d),
-                             float(near_plane), float(far_plane), float(radius_clip), int(tile_size))
+                             float(near_plane), float(far_plane), float(radius_clip), int(tile_size), row0, int(wh))
 
 
 # --------------------------------------------------------------------------- #
@@ -576,6 +618,7 @@ def rasterization(
     rasterize_mode: str = "classic",
     channel_chunk: int = CHANNEL_CHUNK,
     capacity: Optional[RenderCapacity] = None,  # extension: sync-free binning (see RenderCapacity)
+    row_windows=None,  # extension: (row0 i32 [C], window_height) -- camera c renders that row band only (parallel.py)
     **unsupported,
 ) -> Tuple[Tensor, Tensor, Dict]:
     """Drop-in for ``gsplat.rendering.rasterization`` (gsplat==1.1.1) as called at
@@ -596,8 +639,11 @@ def rasterization(
     assert viewmats.shape[-2:] == (4, 4) and Ks.shape[-2:] == (3, 3)
 
     radii, means2d, depths, conics, tiles_per_gauss = fully_fused_projection(
-        means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size)
+        means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
+        row_windows=row_windows)
     C = radii.shape[0]
+    if row_windows is not None:
+        height = int(row_windows[1])  # binning and blend work on C images of width x window_height
     tile_width, tile_height = math.ceil(width / tile_size), math.ceil(height / tile_size)
     with_depth = render_mode in ("RGB+D", "RGB+ED", "D", "ED")
     normalize = render_mode in ("RGB+ED", "ED")

@@ -87,13 +87,14 @@ def render_subexposures(
     combine: bool = True,
     ref_quirk: bool = True,
     capacity=None,  # rendering.RenderCapacity: sync-free tile binning (no device -> host read-back in the step)
+    row_windows=None,  # (row0 i32 [N], window_height): sub-exposure n renders that row band only (parallel.py)
 ) -> Dict[str, Tensor]:
     N = times.reshape(-1).shape[0]
     means, quats = deform_subexposures(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs)
     bg = None if backgrounds is None else backgrounds.expand(N, -1)
     imgs, alphas, meta = rasterization(means=means, quats=quats, scales=scales, opacities=opacities, colors=colors,
                                        backgrounds=bg, viewmats=w2c, Ks=K, width=width, height=height, packed=False,
-                                       render_mode=render_mode, capacity=capacity)
+                                       render_mode=render_mode, capacity=capacity, row_windows=row_windows)
     out = {"exposure_imgs": imgs[:, None], "exposure_alphas": alphas[:, None], "means2d": meta["means2d"],
            "radii": meta["radii"], "meta": meta, "means": means, "quats": quats,
            "pred_sharp_img": imgs[N // 2][None, ..., 0:3]}

@@ -47,14 +47,19 @@ const char *d4_last_error(void);
  * means [*,G,3], quats [*,G,4] wxyz (normalised inside), scales [G,3],
  * viewmats [*,4,4], Ks [*,3,3].
  * out: radii i32 [C,G] (0 = culled), means2d [C,G,2], depths [C,G],
- *      conics [C,G,3], tiles_per_gauss i32 [C,G] (may be NULL).           */
+ *      conics [C,G,3], tiles_per_gauss i32 [C,G] (may be NULL).
+ * cam_row0 (i32 [C], may be NULL) / window_height: per-camera ROW WINDOW for the multi-GPU tile-row bands
+ * (SURVEY 8e): camera c renders rows [cam_row0[c], cam_row0[c] + window_height) of the width x height image.
+ * The projection is that of the full image; means2d.y is returned relative to the window, Gaussians that
+ * cannot touch it get radii = 0, and tile_h must be the window's.  Binning and blend then run on
+ * C images of width x window_height.                                                                    */
 int d4_project_fwd(const float *means, int64_t means_cam_stride, const float *quats,
                    int64_t quats_cam_stride, const float *scales, const float *viewmats,
                    int64_t viewmat_cam_stride, const float *Ks, int64_t k_cam_stride, int C, int G,
                    int width, int height, float eps2d, float near_plane, float far_plane,
                    float radius_clip, int tile_size, int tile_w, int tile_h, int32_t *radii,
                    float *means2d, float *depths, float *conics, int32_t *tiles_per_gauss,
-                   d4_stream_t stream);
+                   const int32_t *cam_row0, int window_height, d4_stream_t stream);
 
 /* ---- a12: projection backward -------------------------------------------------
  * replaces gsplat.fully_fused_projection backward.  v_means [*,G,3] and

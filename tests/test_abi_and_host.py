@@ -44,7 +44,7 @@ def test_argument_errors_are_reported_not_thrown():
     from deblur4dgs_b200 import _cabi
     with pytest.raises(_cabi.D4Error, match="bad sizes"):
         _cabi.call("d4_project_fwd", None, 0, None, 0, None, None, 0, None, 0, 0, 5, 10, 10, 0.3, 0.01, 1e10, 0.0, 16, 1,
-                   1, None, None, None, None, None, None)
+                   1, None, None, None, None, None, None, 0, None)
     with pytest.raises(_cabi.D4Error, match="tile_size 16"):
         _cabi.call("d4_blend_fwd", None, None, None, None, 0, None, None, 1, 1, 3, 32, 32, 8, 4, 4, None, None, 0, 0,
                    None, None, None, None, None, None)

@@ -958,3 +958,51 @@ def test_capacity_mode_equals_sync_mode_and_flags_overflow():
     torch.cuda.synchronize()
     with pytest.raises(D4Error):
         tiny.check()
+
+
+def test_row_window_bands_equal_full_render():
+    """The 2-D multi-GPU partition on ONE GPU: the (sub-exposure, row band) units of all ranks of a 4-rank job,
+    rendered through row windows and put together by parallel.combine_band_units, must reproduce the fused full-frame
+    render (image, alpha) and its parameter gradients.  Band cameras shift the row origin after the projection, so a
+    far-away pixel's dy may round differently: agreement is to fp32 round-off, not bit-exact."""
+    from deblur4dgs_b200.parallel import band_layout, band_units, combine_band_units
+    from deblur4dgs_b200.scene import render_subexposures
+    sc = make_scene(G=30000, width=320, height=200, K=6, N=5, seed=9, scale_mult=1.5)
+    s, scales, opac, colors, bg = _subexposure_inputs(sc, 16)
+    leaves = ["fg_means", "fg_quats", "motion_coefs", "rots", "transls"]
+    world, N, H, W = 4, sc.N, sc.height, sc.width
+    g = torch.Generator().manual_seed(3)
+    w_img, w_acc = torch.randn(1, H, W, 17, generator=g).to(DEV), torch.randn(1, H, W, 1, generator=g).to(DEV)
+    w_img[..., 3] = 0  # the max / min channels may pick another of two near-tied sub-exposures: no cotangent
+    w_img[..., 16] = 0
+
+    def args_of(p, cg):
+        return (p["fg_means"], p["fg_quats"], p["motion_coefs"], s.bg_means, s.bg_quats, p["rots"], p["transls"])
+
+    def fresh():
+        return {k: getattr(s, k).clone().requires_grad_(True) for k in leaves}, colors.clone().requires_grad_(True)
+
+    p0, c0 = fresh()
+    o = render_subexposures(*args_of(p0, c0), s.times, s.RTs, scales, opac, c0, s.w2c, s.K, W, H, backgrounds=bg)
+    ((o["img"] * w_img).sum() + (o["acc"] * w_acc).sum()).backward()
+    band_h, n_bands = band_layout(H, world)
+    p1, c1 = fresh()
+    imgs, alphas, subs, bands = [], [], [], []
+    for rank in range(world):  # what every rank of a 4-rank job would render
+        units = band_units(N, rank, world)
+        idx = torch.as_tensor([u[0] for u in units], device=DEV)
+        row0 = torch.as_tensor([u[1] * band_h for u in units], dtype=torch.int32, device=DEV)
+        ou = render_subexposures(*args_of(p1, c1), s.times[idx], s.RTs[idx], scales, opac, c1, s.w2c, s.K, W, H,
+                                 backgrounds=bg, combine=False, row_windows=(row0, band_h))
+        assert ou["exposure_imgs"].shape == (N, 1, band_h, W, 17)
+        imgs.append(ou["exposure_imgs"]); alphas.append(ou["exposure_alphas"])
+        subs += [u[0] for u in units]; bands += [u[1] for u in units]
+    img, acc = combine_band_units(torch.cat(imgs), torch.cat(alphas), subs, bands, N, n_bands, H, ref_quirk=True)
+    ((img * w_img).sum() + (acc * w_acc).sum()).backward()
+    e_img, e_acc = rel_err(img.detach().cpu().numpy(), o["img"].detach().cpu().numpy()), rel_err(acc.detach().cpu().numpy(), o["acc"].detach().cpu().numpy())
+    gerr = {k: scale_err(p1[k].grad.cpu().numpy(), p0[k].grad.cpu().numpy()) for k in leaves}
+    gerr["colors"] = scale_err(c1.grad.cpu().numpy(), c0.grad.cpu().numpy())
+    report(test="row_window_bands", kind="bands", rel_err_img=e_img, rel_err_acc=e_acc, **gerr)
+    assert e_img <= 1e-5 and e_acc <= 1e-5, (e_img, e_acc)
+    for k, v in gerr.items():
+        assert v <= 1e-5, (k, v)
