@@ -374,39 +374,6 @@ def main():
     if "d4_sort_pairs_u64" in prof:  # radix fallback only: 3 kernels per pass (the default bucketed binning has none)
         launches_per_step += (3 * n_sort_passes - 1) * len(prof["d4_sort_pairs_u64"]) / args.steps
 
-    # ---- timed region 1c (multi-GPU frames runs): STRONG scaling of ONE blurry frame -- BASELINE configs[3] --------
-    # the frame's N x world (sub-exposure, tile-row band) units over the ranks, image / extrema / gradient all-reduce
-    strong = None
-    if world > 1 and args.shard == "frames":
-        sc_frame = make_config(args.config, seed=seed).to(dev) if not args.checkpoint else sc  # the SAME frame on every rank
-        for _ in range(max(3, args.warmup)):
-            step(sc_frame, shard="bands")
-        torch.cuda.synchronize()
-        cprof = {}
-        parallel.PROFILE = cprof
-        dist.barrier()
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(args.steps):
-            step(sc_frame, shard="bands")
-        s1.record()
-        dist.barrier()
-        torch.cuda.synchronize()
-        parallel.PROFILE = None
-        if cap_bands is not None:
-            cap_bands.check()
-        coll = sum(a.elapsed_time(b) for v in cprof.values() for a, b in v) / args.steps
-        t = torch.tensor([s0.elapsed_time(s1), coll], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        strong_ms = float(t[0].item()) / args.steps
-        strong = {"partition": f"{N} sub-exposures x {world} tile-row bands, {N} units per rank", "frames_per_s": N / (strong_ms * 1e-3),
-                  "ms_per_blurry_frame": strong_ms, "speedup_vs_1gpu": (ms_total / args.steps) / strong_ms,
-                  "collective_ms": float(t[1].item()),
-                  "collectives": {k: len(v) / args.steps for k, v in cprof.items()},
-                  "note": "speedup against this run's own one-frame-per-GPU step (ms_per_step, which includes the gradient "
-                          "all-reduce); collective_ms = CUDA-event time inside the NCCL calls (max over ranks)"}
-
     # ---- timed region 2: end to end through the public API with HOST buffers --------------
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -487,6 +454,43 @@ def main():
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = frames_per_step_global * args.steps / (float(ms2.item()) * 1e-3)
+
+    # ---- timed region 3 (multi-GPU frames runs): STRONG scaling of ONE blurry frame -- BASELINE configs[3] --------
+    # the frame's N x world (sub-exposure, tile-row band) units over the ranks, image / extrema / gradient all-reduce
+    strong = None
+    if world > 1 and args.shard == "frames":
+        sc_frame = make_config(args.config, seed=seed).to(dev) if not args.checkpoint else sc  # the SAME frame on every rank
+        for _ in range(max(3, args.warmup)):
+            step(sc_frame, shard="bands")
+        torch.cuda.synchronize()
+        cprof, kprof = {}, {}
+        parallel.PROFILE = cprof
+        _cabi.PROFILE = kprof
+        dist.barrier()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            step(sc_frame, shard="bands")
+        s1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        parallel.PROFILE = None
+        _cabi.PROFILE = None
+        if cap_bands is not None:
+            cap_bands.check()
+        coll = sum(a.elapsed_time(b) for v in cprof.values() for a, b in v) / args.steps
+        t = torch.tensor([s0.elapsed_time(s1), coll], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong_ms = float(t[0].item()) / args.steps
+        strong = {"partition": f"{N} sub-exposures x {world} tile-row bands, {N} units per rank", "frames_per_s": N / (strong_ms * 1e-3),
+                  "ms_per_blurry_frame": strong_ms, "speedup_vs_1gpu": (ms_total / args.steps) / strong_ms,
+                  "collective_ms": float(t[1].item()),
+                  "collectives": {k: len(v) / args.steps for k, v in cprof.items()},
+                  "collective_ms_by_tag": {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in cprof.items()},
+                  "kernel_ms_per_step": {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in kprof.items()},
+                  "note": "speedup against this run's own one-frame-per-GPU step (ms_per_step, which includes the gradient "
+                          "all-reduce); collective_ms = CUDA-event time inside the NCCL calls (max over ranks)"}
 
     if rank == 0:
         value = frames_per_step_global * args.steps / (ms_total * 1e-3)

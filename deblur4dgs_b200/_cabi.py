@@ -54,6 +54,10 @@ PROTOTYPES = {
     "d4_assemble_fwd": (c_int, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P]),
     "d4_assemble_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, P]),
     "d4_densify_stats": (c_int, [P, P, I, I, F, F, F, P, P, P, P]),
+    "d4_band_partial": (c_int, [P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P]),
+    "d4_band_winner": (c_int, [P, P, P, I, I, I, I, I, I, I, I, P, P, P]),
+    "d4_band_finalize": (c_int, [P, P, P, I, I, I, I, I, I, I, P, P, P]),
+    "d4_band_bwd": (c_int, [P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P, P]),
     "d4_combine_fwd": (c_int, [P, P, I, L, I, I, I, I, P, P, P, P, P]),
     "d4_combine_bwd": (c_int, [P, P, I, L, I, I, I, P, P, P, P, P]),
 }

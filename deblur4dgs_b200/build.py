@@ -31,6 +31,7 @@ UNITS = {
     "blend_slab_bwd.cu": [],
     "deform.cu": [],
     "combine.cu": [],
+    "band_combine.cu": [],
     "camera.cu": [],
     "assemble.cu": [],
 }

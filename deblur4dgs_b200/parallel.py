@@ -170,9 +170,16 @@ def band_units(n_sub: int, rank: int, world: int) -> List[tuple]:
     return units[rank * n_sub:(rank + 1) * n_sub]
 
 
+def _i32_array(xs):
+    import ctypes
+    return (ctypes.c_int32 * max(len(xs), 1))(*xs)
+
+
 class _BandCombine(torch.autograd.Function):
     """N-way combine (scene_model.py:386-397) over units spread across ranks.  imgs [U,1,band_h,W,D], alphas
-    [U,1,band_h,W,1] are this rank's units, ``subs`` / ``bands`` their coordinates."""
+    [U,1,band_h,W,1] are this rank's units, ``subs`` / ``bands`` their coordinates.  CUDA tensors go through the
+    d4_band_* kernels (csrc/band_combine.cu); the torch expressions of the same steps below serve the world-size-2 gloo
+    tests of this host logic on CPU tensors (tests/test_parallel_gloo.py) and are the kernels' reference."""
 
     @staticmethod
     def forward(ctx, imgs, alphas, subs, bands, n_sub, n_bands, height, max_ch, min_ch, ref_quirk, group):
@@ -180,40 +187,62 @@ class _BandCombine(torch.autograd.Function):
         dev, dt = imgs.device, imgs.dtype
         Hp = n_bands * bh
         n_ext = n_sub - 1 if ref_quirk else n_sub  # extrema over r_0 .. r_{N-2} (+ the mean) in quirk mode
+        distributed = dist.is_initialized() and dist.get_world_size(group) > 1
+        if imgs.is_cuda:
+            from ._cabi import call, check_tensors, ptr, stream_ptr
+            check_tensors(imgs, alphas, what="band combine")
+            imgs, alphas = imgs.float().contiguous(), alphas.float().contiguous()
+            c_subs, c_bands = _i32_array(subs), _i32_array(bands)
+            part = torch.empty((Hp, W, D + 1), dtype=torch.float32, device=dev)
+            ext = torch.empty((Hp, W, 2), dtype=torch.float32, device=dev)
+            call("d4_band_partial", ptr(imgs), ptr(alphas), c_subs, c_bands, U, n_sub, n_ext, n_bands, bh, W, D, max_ch,
+                 min_ch, ptr(part), ptr(ext), stream_ptr())
+            if distributed:
+                _all_reduce(part, dist.ReduceOp.SUM, group, "image_sum")
+                _all_reduce(ext, dist.ReduceOp.MAX, group, "extrema_max")
+            winner = torch.empty((Hp, W, 2), dtype=torch.int32, device=dev)
+            call("d4_band_winner", ptr(imgs), c_subs, c_bands, U, n_ext, n_bands, bh, W, D, max_ch, min_ch, ptr(ext),
+                 ptr(winner), stream_ptr())
+            if distributed:
+                _all_reduce(winner, dist.ReduceOp.MIN, group, "winner_min")
+            out = torch.empty((1, height, W, D), dtype=torch.float32, device=dev)
+            out_alpha = torch.empty((1, height, W, 1), dtype=torch.float32, device=dev)
+            call("d4_band_finalize", ptr(part), ptr(ext), ptr(winner), height, W, D, max_ch, min_ch, int(ref_quirk), n_ext,
+                 ptr(out), ptr(out_alpha), stream_ptr())
+            ctx.save_for_backward(winner)
+            ctx.cfg = (subs, bands, n_sub, n_bands, bh, height, (max_ch, min_ch), imgs.shape, alphas.shape)
+            return out, out_alpha
         part = torch.zeros((Hp, W, D + 1), dtype=dt, device=dev)
-        chans = [c for c in (max_ch, min_ch) if 0 <= c < D]
-        sign = {max_ch: 1.0, min_ch: -1.0}
-        ext = torch.full((Hp, W, max(len(chans), 1)), float("-inf"), dtype=dt, device=dev)
+        chans = [(0, max_ch, 1.0), (1, min_ch, -1.0)]
+        chans = [c for c in chans if 0 <= c[1] < D]
+        ext = torch.full((Hp, W, 2), float("-inf"), dtype=dt, device=dev)
         for u in range(U):
             rows = slice(bands[u] * bh, (bands[u] + 1) * bh)
             part[rows, :, :D] += imgs[u, 0] / n_sub
             part[rows, :, D:] += alphas[u, 0] / n_sub
             if subs[u] < n_ext:
-                for j, ch in enumerate(chans):
-                    ext[rows, :, j] = torch.maximum(ext[rows, :, j], sign[ch] * imgs[u, 0, :, :, ch])
-        distributed = dist.is_initialized() and dist.get_world_size(group) > 1
+                for j, ch, sg in chans:
+                    ext[rows, :, j] = torch.maximum(ext[rows, :, j], sg * imgs[u, 0, :, :, ch])
         if distributed:
             _all_reduce(part, dist.ReduceOp.SUM, group, "image_sum")
-            if chans:
-                _all_reduce(ext, dist.ReduceOp.MAX, group, "extrema_max")
+            _all_reduce(ext, dist.ReduceOp.MAX, group, "extrema_max")
         # first sub-exposure attaining the extremum (torch.max / min(dim) semantics), agreed on globally
-        big = 2 ** 30
-        winner = torch.full(ext.shape, big, dtype=torch.int32, device=dev)
+        winner = torch.full(ext.shape, 2 ** 30, dtype=torch.int32, device=dev)
         for u in range(U):
             if subs[u] < n_ext:
                 rows = slice(bands[u] * bh, (bands[u] + 1) * bh)
-                for j, ch in enumerate(chans):
-                    hit = (sign[ch] * imgs[u, 0, :, :, ch]) == ext[rows, :, j]
+                for j, ch, sg in chans:
+                    hit = (sg * imgs[u, 0, :, :, ch]) == ext[rows, :, j]
                     winner[rows, :, j] = torch.where(hit, torch.clamp(winner[rows, :, j], max=subs[u]), winner[rows, :, j])
-        if distributed and chans:
+        if distributed:
             _all_reduce(winner, dist.ReduceOp.MIN, group, "winner_min")
         out = part[:height, :, :D].clone()
         out_alpha = part[:height, :, D:].clone()
-        for j, ch in enumerate(chans):
-            best = sign[ch] * ext[:height, :, j]
+        for j, ch, sg in chans:
+            best = sg * ext[:height, :, j]
             mean = out[:, :, ch]
             if ref_quirk:
-                mean_wins = (mean > best) if ch == max_ch else (mean < best)
+                mean_wins = (mean > best) if j == 0 else (mean < best)
                 if n_ext == 0:
                     mean_wins = torch.ones_like(mean_wins)
                 winner[:height, :, j] = torch.where(mean_wins, torch.full_like(winner[:height, :, j], -1), winner[:height, :, j])
@@ -221,16 +250,26 @@ class _BandCombine(torch.autograd.Function):
             else:
                 out[:, :, ch] = best
         ctx.save_for_backward(winner)
-        ctx.cfg = (subs, bands, n_sub, bh, height, chans, imgs.shape, alphas.shape)
+        ctx.cfg = (subs, bands, n_sub, n_bands, bh, height, (max_ch, min_ch), imgs.shape, alphas.shape)
         return out[None], out_alpha[None]
 
     @staticmethod
     def backward(ctx, v_out, v_alpha):
         (winner,) = ctx.saved_tensors
-        subs, bands, n_sub, bh, height, chans, ishape, ashape = ctx.cfg
+        subs, bands, n_sub, n_bands, bh, height, (max_ch, min_ch), ishape, ashape = ctx.cfg
         U, _, _, W, D = ishape
         dev = winner.device
         Hp = winner.shape[0]
+        if winner.is_cuda:
+            from ._cabi import call, ptr, stream_ptr
+            v_out = v_out.float().contiguous() if v_out is not None else torch.zeros((1, height, W, D), device=dev)
+            v_alpha = v_alpha.float().contiguous() if v_alpha is not None else torch.zeros((1, height, W, 1), device=dev)
+            v_imgs = torch.empty(ishape, dtype=torch.float32, device=dev)
+            v_alphas = torch.empty(ashape, dtype=torch.float32, device=dev)
+            call("d4_band_bwd", ptr(winner), _i32_array(subs), _i32_array(bands), U, n_sub, n_bands, bh, W, D, height,
+                 max_ch, min_ch, ptr(v_out), ptr(v_alpha), ptr(v_imgs), ptr(v_alphas), stream_ptr())
+            return v_imgs, v_alphas, None, None, None, None, None, None, None, None, None
+        chans = [c for c in ((0, max_ch), (1, min_ch)) if 0 <= c[1] < D]
         vo = torch.zeros((Hp, W, D), dtype=torch.float32, device=dev)
         va = torch.zeros((Hp, W, 1), dtype=torch.float32, device=dev)
         if v_out is not None:
@@ -243,7 +282,7 @@ class _BandCombine(torch.autograd.Function):
             rows = slice(bands[u] * bh, (bands[u] + 1) * bh)
             v_imgs[u, 0] = vo[rows] / n_sub
             v_alphas[u, 0] = va[rows] / n_sub
-            for j, ch in enumerate(chans):
+            for j, ch in chans:
                 w = winner[rows, :, j]
                 routed = torch.where(w == subs[u], vo[rows, :, ch], torch.zeros_like(vo[rows, :, ch]))
                 v_imgs[u, 0, :, :, ch] = torch.where(w < 0, vo[rows, :, ch] / n_sub, routed)  # -1: the mean itself won

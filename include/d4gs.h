@@ -277,6 +277,26 @@ int d4_combine_bwd(const uint8_t *arg_max, const uint8_t *arg_min, int N, int64_
                    int min_ch, const float *v_out_img, const float *v_out_alpha, float *v_imgs,
                    float *v_alphas, d4_stream_t stream);
 
+/* ---- a13 for the 2-D multi-GPU partition: the same combine over (sub-exposure, tile-row band) units
+ * spread across ranks.  A rank holds U units imgs [U,bh,W,D] / alphas [U,bh,W] with host-side coordinates subs /
+ * bands (HOST int arrays, U <= 32).  d4_band_partial -> part [n_bands*bh, W, D+1] (sum of img / n_sub, alpha plane
+ * as channel D) and ext [n_bands*bh, W, 2] (max of the max_ch value and of minus the min_ch value over the units with
+ * sub < n_ext; -inf where the rank has none); the caller all-reduces part (SUM) and ext (MAX).  d4_band_winner ->
+ * winner i32 [.., 2]: lowest sub-exposure among the rank's units attaining the global extremum (2^30 if none); the
+ * caller all-reduces it (MIN).  d4_band_finalize -> out_img [H,W,D], out_alpha [H,W]; ref_quirk as d4_combine_fwd
+ * (winner := -1 where the mean itself wins).  d4_band_bwd routes v_out / v_alpha to v_imgs / v_alphas (overwritten). */
+int d4_band_partial(const float *imgs, const float *alphas, const int32_t *subs, const int32_t *bands, int U,
+                    int n_sub, int n_ext, int n_bands, int bh, int W, int D, int max_ch, int min_ch,
+                    float *part, float *ext, d4_stream_t stream);
+int d4_band_winner(const float *imgs, const int32_t *subs, const int32_t *bands, int U, int n_ext, int n_bands,
+                   int bh, int W, int D, int max_ch, int min_ch, const float *ext, int32_t *winner,
+                   d4_stream_t stream);
+int d4_band_finalize(const float *part, const float *ext, int32_t *winner, int H, int W, int D, int max_ch,
+                     int min_ch, int ref_quirk, int n_ext, float *out_img, float *out_alpha, d4_stream_t stream);
+int d4_band_bwd(const int32_t *winner, const int32_t *subs, const int32_t *bands, int U, int n_sub, int n_bands,
+                int bh, int W, int D, int H, int max_ch, int min_ch, const float *v_out, const float *v_alpha,
+                float *v_imgs, float *v_alphas, d4_stream_t stream);
+
 /* ---- f1 ("next" row): activations + fg|bg concatenation + feature-vector assembly ------------------
  * replaces GaussianParams' activations (params.py:39-43, 70-84: exp / sigmoid / sigmoid), the fg|bg
  * torch.cat of SceneModel.get_*_all (scene_model.py:122-143) and the colors_override assembly

@@ -1006,3 +1006,33 @@ def test_row_window_bands_equal_full_render():
     assert e_img <= 1e-5 and e_acc <= 1e-5, (e_img, e_acc)
     for k, v in gerr.items():
         assert v <= 1e-5, (k, v)
+
+
+def test_band_combine_kernels_equal_host_expressions():
+    """csrc/band_combine.cu against the torch expressions of parallel._BandCombine (which the gloo tests pin to the
+    literal reference combine): values, winners through exact ties, gradients, both quirk modes."""
+    from deblur4dgs_b200.parallel import band_layout, band_units, combine_band_units
+    N, H, W, D, world = 5, 40, 9, 17, 3
+    band_h, n_bands = band_layout(H, world)
+    Hp = band_h * n_bands
+    g = torch.Generator().manual_seed(2)
+    full = torch.randn(N, 1, Hp, W, D, generator=g)
+    full[..., 3] = (torch.rand(N, 1, Hp, W, generator=g) > 0.6).float()
+    full[:, :, :, :3, 16] = 0.0
+    full[:, :, :10, :, 3] = 0.0
+    falpha = torch.rand(N, 1, Hp, W, 1, generator=g)
+    vi, va = torch.randn(1, H, W, D, generator=g), torch.randn(1, H, W, 1, generator=g)
+    for rank in range(world):
+        units = band_units(N, rank, world)
+        subs, bands = [u[0] for u in units], [u[1] for u in units]
+        li = torch.stack([full[s, :, b * band_h:(b + 1) * band_h] for s, b in units])
+        la = torch.stack([falpha[s, :, b * band_h:(b + 1) * band_h] for s, b in units])
+        for quirk in (True, False):
+            res = []
+            for dev in ("cpu", DEV):
+                a, b = li.detach().clone().to(dev).requires_grad_(True), la.detach().clone().to(dev).requires_grad_(True)
+                out, oa = combine_band_units(a, b, subs, bands, N, n_bands, H, ref_quirk=quirk)
+                ((out * vi.to(dev)).sum() + (oa * va.to(dev)).sum()).backward()
+                res.append([t.detach().cpu() for t in (out, oa, a.grad, b.grad)])
+            for x, y in zip(*res):
+                assert torch.allclose(x, y, atol=1e-6), (rank, quirk)
