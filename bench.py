@@ -272,15 +272,16 @@ def main():
                                                   extra=scn.extra_channels if scn.extra_channels.shape[1] else None,
                                                   with_mask=True)
 
-        def local(times, RTs, combine, row_windows=None):
+        def local(times, RTs, combine, row_windows=None, camera_of=None):
             return render_subexposures(p["fg_means"], p["fg_quats"], p["motion_coefs"], p["bg_means"], p["bg_quats"],
                                        p["rots"], p["transls"], times, RTs, scales, opac, colors, scn.w2c, scn.K, W, H,
                                        backgrounds=bg, render_mode="RGB+ED", combine=combine, ref_quirk=True,
-                                       capacity=cap if row_windows is None else cap_bands, row_windows=row_windows)
+                                       capacity=cap if row_windows is None else cap_bands, row_windows=row_windows,
+                                       camera_of=camera_of)
 
         if world > 1 and shard == "bands":
-            def render_units(t, r, row0, band_h):
-                o = local(t, r, False, (row0, band_h))
+            def render_units(t, r, camera_of, row0, band_h):
+                o = local(t, r, False, (row0, band_h), camera_of)
                 return o["exposure_imgs"], o["exposure_alphas"]
             img, acc = render_frame_banded(scn.times, scn.RTs, H, render_units, ref_quirk=True)
         elif world > 1 and shard == "subexposures":

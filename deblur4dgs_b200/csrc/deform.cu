@@ -163,6 +163,9 @@ __device__ __forceinline__ void rt_backward(const float *__restrict__ RT, const 
     }
 }
 
+constexpr int kDefStride = kDefThreads + 1;  // row stride of the backward's [K][threads] / [9][threads] tiles: a thread's own
+                                             // column and a (k, j) thread's walk along a row are both bank-conflict free
+
 __global__ void __launch_bounds__(kDefThreads)
 deform_fg_bwd_kernel(const float *__restrict__ fg_means, const float *__restrict__ fg_quats,
                      const float *__restrict__ coefs_raw, const float *__restrict__ rots,
@@ -172,11 +175,15 @@ deform_fg_bwd_kernel(const float *__restrict__ fg_means, const float *__restrict
                      float *__restrict__ v_fg_means, float *__restrict__ v_fg_quats,
                      float *__restrict__ v_coefs_raw, float *__restrict__ v_rots,
                      float *__restrict__ v_transls, float *__restrict__ v_times, float *__restrict__ v_RTs) {
+    // Per Gaussian and timestamp: hand-derived reverse-mode VJP of deform_point (deform_math.cuh).  The basis gradient
+    // v_B[k][j] = sum_g c_gk * v_blend_gj is a [K x 128] x [128 x 9] product per CTA and timestamp: the coefficients
+    // already sit in shared memory, the 9 blend cotangents are parked next to them, and K*9 threads each walk one
+    // (k, j) row pair -- no warp shuffles, one global atomic per (CTA, timestamp, k, j, frame).
     extern __shared__ float smem[];
-    float *s_coef_all = smem;                          // [K][kDefThreads] softmaxed coefficients
-    float *s_vcoef_all = smem + K * kDefThreads;       // [K][kDefThreads] dL/dcoef
-    float *s_vB = smem + 2 * K * kDefThreads;          // [K][9]   sum_g c_k * v_blend_j   (current n)
-    float *s_red = s_vB + K * 9;                       // [16]     12 camera entries + time gradient
+    float *s_coef_all = smem;                          // [K][kDefStride] softmaxed coefficients
+    float *s_vcoef_all = smem + K * kDefStride;        // [K][kDefStride] dL/dcoef
+    float *s_vb = smem + 2 * K * kDefStride;           // [9][kDefStride] blend cotangents of the current timestamp
+    float *s_red = s_vb + 9 * kDefStride;              // [16]     12 camera entries + time gradient
     const int tid = threadIdx.x, lane = tid & 31;
     const int g = blockIdx.x * kDefThreads + tid;
     const bool active = g < Gf;
@@ -184,19 +191,32 @@ deform_fg_bwd_kernel(const float *__restrict__ fg_means, const float *__restrict
     float *s_vcoef = s_vcoef_all + tid;
     float mu[3] = {0.f, 0.f, 0.f}, q[4] = {1.f, 0.f, 0.f, 0.f};
     if (active) {
-        softmax_coefs(coefs_raw + (int64_t)g * K, K, s_coef);
+        // softmax over K raw logits (as softmax_coefs, with the padded stride)
+        const float *raw = coefs_raw + (int64_t)g * K;
+        float mx = -INFINITY;
+        for (int k = 0; k < K; ++k) {
+            const float v = __ldg(raw + k);
+            s_coef[k * kDefStride] = v;
+            mx = fmaxf(mx, v);
+        }
+        float sum = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float e = expf(s_coef[k * kDefStride] - mx);
+            s_coef[k * kDefStride] = e;
+            sum += e;
+        }
+        for (int k = 0; k < K; ++k) s_coef[k * kDefStride] = s_coef[k * kDefStride] / sum;
         mu[0] = __ldg(fg_means + 3LL * g); mu[1] = __ldg(fg_means + 3LL * g + 1); mu[2] = __ldg(fg_means + 3LL * g + 2);
         float4 q4 = __ldg(reinterpret_cast<const float4 *>(fg_quats) + g);
         q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
     } else {
-        for (int k = 0; k < K; ++k) s_coef[k * kDefThreads] = 0.f;
+        for (int k = 0; k < K; ++k) s_coef[k * kDefStride] = 0.f;
     }
-    for (int k = 0; k < K; ++k) s_vcoef[k * kDefThreads] = 0.f;
+    for (int k = 0; k < K; ++k) s_vcoef[k * kDefStride] = 0.f;
     float v_mu[3] = {0.f, 0.f, 0.f}, v_q[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int n = 0; n < N; ++n) {
-        for (int e = tid; e < K * 9 + 16; e += kDefThreads) s_vB[e] = 0.f;  // s_red follows s_vB
-        __syncthreads();
+        if (tid < 16) s_red[tid] = 0.f;
         const FramePair f = frame_pair(__ldg(times + n), T);
         const float *RT = RTs ? RTs + 12LL * n : nullptr;
         float vb[9];
@@ -206,39 +226,41 @@ deform_fg_bwd_kernel(const float *__restrict__ fg_means, const float *__restrict
 #pragma unroll
         for (int j = 0; j < 16; ++j) r16[j] = 0.f;
         if (active) {
+            // blended (transl 3, rot6d 6) at the two frames
             float bp[9], bn[9], bl[9];
-            blend_bases(s_coef, K, T, f.pre, rots, transls, bp);
-            blend_bases(s_coef, K, T, f.nxt, rots, transls, bn);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) bp[j] = bn[j] = 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float ck = s_coef[k * kDefStride];
+                const float *tp = transls + ((int64_t)k * T + f.pre) * 3, *tn = transls + ((int64_t)k * T + f.nxt) * 3;
+                const float *rp = rots + ((int64_t)k * T + f.pre) * 6, *rn = rots + ((int64_t)k * T + f.nxt) * 6;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) bp[j] += ck * __ldg(tp + j), bn[j] += ck * __ldg(tn + j);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) bp[3 + j] += ck * __ldg(rp + j), bn[3 + j] += ck * __ldg(rn + j);
+            }
 #pragma unroll
             for (int j = 0; j < 9; ++j) bl[j] = (1.0f - f.w) * bp[j] + f.w * bn[j];
             const float *vmp = v_out_means + ((int64_t)n * G + g) * 3;
             const float vm[3] = {__ldg(vmp), __ldg(vmp + 1), __ldg(vmp + 2)};
             const float4 vq4 = __ldg(reinterpret_cast<const float4 *>(v_out_quats) + (int64_t)n * G + g);
             const float vq[4] = {vq4.x, vq4.y, vq4.z, vq4.w};
-            // dual evaluation: inputs 0-2 tl, 3-8 r6, 9-11 mu, 12-15 q_raw
-            typedef Dual<16> DU;
-            DU in[16];
+            // camera delta backward: v_mu' = R_rt^T v
+            float vmu[3] = {vm[0], vm[1], vm[2]};
+            if (RT != nullptr) {
 #pragma unroll
-            for (int a = 0; a < 16; ++a) {
-#pragma unroll
-                for (int b2 = 0; b2 < 16; ++b2) in[a].d[b2] = (a == b2) ? 1.f : 0.f;
+                for (int j = 0; j < 3; ++j) vmu[j] = __ldg(RT + j) * vm[0] + __ldg(RT + 4 + j) * vm[1] + __ldg(RT + 8 + j) * vm[2];
             }
+            float grad[16], mprime[3];
+            deform_point_vjp(bl, bl + 3, mu, q, vmu, vq, mprime, grad);
+            if (RT != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) in[j].v = bl[j];
+                for (int i = 0; i < 3; ++i) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) in[9 + j].v = mu[j];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) in[12 + j].v = q[j];
-            DU om[3], oq[4];
-            deform_point<DU>(in, in + 3, in + 9, in + 12, om, oq);
-            const float mprime[3] = {om[0].v, om[1].v, om[2].v};
-            float vmu[3];
-            rt_backward(RT, vm, mprime, vmu, r16);
-            float grad[16];
-#pragma unroll
-            for (int a = 0; a < 16; ++a)
-                grad[a] = vmu[0] * om[0].d[a] + vmu[1] * om[1].d[a] + vmu[2] * om[2].d[a] + vq[0] * oq[0].d[a] +
-                          vq[1] * oq[1].d[a] + vq[2] * oq[2].d[a] + vq[3] * oq[3].d[a];
+                    for (int j = 0; j < 3; ++j) r16[4 * i + j] = vm[i] * mprime[j];
+                    r16[4 * i + 3] = vm[i];
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 9; ++j) vb[j] = grad[j];
 #pragma unroll
@@ -259,28 +281,30 @@ deform_fg_bwd_kernel(const float *__restrict__ fg_means, const float *__restrict
                 for (int j = 0; j < 3; ++j) acc += ((1.0f - f.w) * __ldg(tp + j) + f.w * __ldg(tn + j)) * vb[j];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) acc += ((1.0f - f.w) * __ldg(rp + j) + f.w * __ldg(rn + j)) * vb[3 + j];
-                s_vcoef[k * kDefThreads] += acc;
+                s_vcoef[k * kDefStride] += acc;
             }
         }
-        // reductions over the Gaussians of this CTA (all lanes participate)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) s_vb[j * kDefStride + tid] = vb[j];
+        __syncthreads();  // s_vb complete, s_red zeroed
+        // camera-delta and time gradients: transposing butterfly over the warp, then one shared atomic per value
         warp_transpose_reduce_d<16>(r16, lane);
         if (lane < 16 && r16[0] != 0.f) atomicAdd(&s_red[lane], r16[0]);
-        for (int k = 0; k < K; ++k) {
-            const float ck = s_coef[k * kDefThreads];
-            float r[16];
-#pragma unroll
-            for (int j = 0; j < 9; ++j) r[j] = ck * vb[j];
-#pragma unroll
-            for (int j = 9; j < 16; ++j) r[j] = 0.f;
-            warp_transpose_reduce_d<16>(r, lane);
-            if (lane < 9 && r[0] != 0.f) atomicAdd(&s_vB[k * 9 + lane], r[0]);
-        }
-        __syncthreads();
-        // flush: bases at pre get (1-w), at next get w
+        // basis gradients: thread (k, j) sums c_gk * vb_gj over the CTA's Gaussians
         for (int e = tid; e < K * 9; e += kDefThreads) {
-            const float val = s_vB[e];
-            if (val == 0.f) continue;
             const int k = e / 9, jj = e - 9 * k;
+            const float *cr = s_coef_all + k * kDefStride, *vr = s_vb + jj * kDefStride;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+            for (int t = 0; t < kDefThreads; t += 4) {
+                a0 = fmaf(cr[t], vr[t], a0);
+                a1 = fmaf(cr[t + 1], vr[t + 1], a1);
+                a2 = fmaf(cr[t + 2], vr[t + 2], a2);
+                a3 = fmaf(cr[t + 3], vr[t + 3], a3);
+            }
+            const float val = (a0 + a1) + (a2 + a3);
+            if (val == 0.f) continue;
+            // bases at the floor frame get (1 - w), at the ceil frame w
             if (jj < 3) {
                 atomicAdd(v_transls + ((int64_t)k * T + f.pre) * 3 + jj, (1.0f - f.w) * val);
                 atomicAdd(v_transls + ((int64_t)k * T + f.nxt) * 3 + jj, f.w * val);
@@ -289,18 +313,19 @@ deform_fg_bwd_kernel(const float *__restrict__ fg_means, const float *__restrict
                 atomicAdd(v_rots + ((int64_t)k * T + f.nxt) * 6 + (jj - 3), f.w * val);
             }
         }
+        __syncthreads();  // s_red complete; every (k, j) thread is done with s_vb
         if (tid < 12 && v_RTs && s_red[tid] != 0.f) atomicAdd(v_RTs + 12LL * n + tid, s_red[tid]);
         if (tid == 15 && s_red[15] != 0.f) atomicAdd(v_times + n, s_red[15]);
-        __syncthreads();
+        __syncthreads();  // s_red read before the next timestamp zeroes it
     }
     if (active) {
         v_fg_means[3LL * g] = v_mu[0]; v_fg_means[3LL * g + 1] = v_mu[1]; v_fg_means[3LL * g + 2] = v_mu[2];
         reinterpret_cast<float4 *>(v_fg_quats)[g] = make_float4(v_q[0], v_q[1], v_q[2], v_q[3]);
         // softmax backward: v_raw_k = c_k (v_c_k - sum_m c_m v_c_m)
         float dotp = 0.f;
-        for (int k = 0; k < K; ++k) dotp += s_coef[k * kDefThreads] * s_vcoef[k * kDefThreads];
+        for (int k = 0; k < K; ++k) dotp += s_coef[k * kDefStride] * s_vcoef[k * kDefStride];
         for (int k = 0; k < K; ++k)
-            v_coefs_raw[(int64_t)g * K + k] = s_coef[k * kDefThreads] * (s_vcoef[k * kDefThreads] - dotp);
+            v_coefs_raw[(int64_t)g * K + k] = s_coef[k * kDefStride] * (s_vcoef[k * kDefStride] - dotp);
     }
 }
 
@@ -569,7 +594,7 @@ extern "C" int d4_deform_bwd(const float *fg_means, const float *fg_quats, const
                          v_motion_coefs && v_rots && v_transls && v_times && ((uintptr_t)fg_quats & 15) == 0 &&
                          ((uintptr_t)v_fg_quats & 15) == 0,
                      "d4_deform_bwd: null/unaligned fg pointer");
-        size_t smem = sizeof(float) * (2 * K * kDefThreads + K * 9 + 16);
+        size_t smem = sizeof(float) * ((2 * K + 9) * kDefStride + 16);
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(deform_fg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         deform_fg_bwd_kernel<<<cdiv(Gf, kDefThreads), kDefThreads, smem, as_stream(stream)>>>(

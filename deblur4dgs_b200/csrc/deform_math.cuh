@@ -168,4 +168,162 @@ D4_HD void deform_point(const S *tl, const S *r6, const S *mu, const S *qraw, S 
     oq[0] = w / on; oq[1] = vx / on; oq[2] = vy / on; oq[3] = vz / on;
 }
 
+// Reverse-mode vector-Jacobian product of deform_point, derived by hand (cotangents v_om[3], v_oq[4] of the
+// outputs -> grad[16] = cotangents of (tl 3, r6 6, mu 3, q_raw 4)): one forward recomputation plus ~250 flops,
+// against ~2 000 for the 16-partial forward-mode evaluation above.  tests/test_host_math.py checks it against the
+// Dual<16> evaluation of the same code (all four rotation-matrix -> quaternion branches) on the CPU.
+D4_HD void deform_point_vjp(const float *tl, const float *r6, const float *mu, const float *qraw, const float *v_om,
+                            const float *v_oq, float *om_out, float *grad) {
+    const float eps = 1e-12f;
+    (void)tl;
+    // ---- forward recomputation (same order of operations as deform_point<float>)
+    const float qn = sqrtf(qraw[0] * qraw[0] + qraw[1] * qraw[1] + qraw[2] * qraw[2] + qraw[3] * qraw[3]);
+    const float qd = qn >= eps ? qn : eps;
+    const float qh[4] = {qraw[0] / qd, qraw[1] / qd, qraw[2] / qd, qraw[3] / qd};
+    const float *a = r6, *b = r6 + 3;
+    const float an_raw = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    const float an = an_raw >= eps ? an_raw : eps;
+    const float x[3] = {a[0] / an, a[1] / an, a[2] / an};
+    const float bx = b[0] * x[0] + b[1] * x[1] + b[2] * x[2];
+    const float yp[3] = {b[0] - bx * x[0], b[1] - bx * x[1], b[2] - bx * x[2]};
+    const float yn_raw = sqrtf(yp[0] * yp[0] + yp[1] * yp[1] + yp[2] * yp[2]);
+    const float yn = yn_raw >= eps ? yn_raw : eps;
+    const float y[3] = {yp[0] / yn, yp[1] / yn, yp[2] / yn};
+    const float z[3] = {x[1] * y[2] - x[2] * y[1], x[2] * y[0] - x[0] * y[2], x[0] * y[1] - x[1] * y[0]};
+    if (om_out) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) om_out[i] = x[i] * mu[0] + y[i] * mu[1] + z[i] * mu[2] + tl[i];
+    }
+    const float tr = x[0] + y[1] + z[2];
+    int choice = 0;
+    float best = x[0];
+    if (y[1] > best) { best = y[1]; choice = 1; }
+    if (z[2] > best) { best = z[2]; choice = 2; }
+    if (tr > best) { best = tr; choice = 3; }
+    float p[4];
+    if (choice == 3) {
+        p[0] = y[2] - z[1]; p[1] = z[0] - x[2]; p[2] = x[1] - y[0]; p[3] = 1.0f + tr;
+    } else if (choice == 0) {
+        p[0] = 1.0f - tr + 2.0f * x[0]; p[1] = x[1] + y[0]; p[2] = x[2] + z[0]; p[3] = y[2] - z[1];
+    } else if (choice == 1) {
+        p[1] = 1.0f - tr + 2.0f * y[1]; p[2] = y[2] + z[1]; p[0] = y[0] + x[1]; p[3] = z[0] - x[2];
+    } else {
+        p[2] = 1.0f - tr + 2.0f * z[2]; p[0] = z[0] + x[2]; p[1] = z[1] + y[2]; p[3] = x[1] - y[0];
+    }
+    const float pn = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+    const float ph[4] = {p[0] / pn, p[1] / pn, p[2] / pn, p[3] / pn};
+    const float qx = qh[1], qy = qh[2], qz = qh[3], qw = qh[0];
+    const float ux = ph[3] * qx + qw * ph[0] + (ph[1] * qz - ph[2] * qy);
+    const float uy = ph[3] * qy + qw * ph[1] + (ph[2] * qx - ph[0] * qz);
+    const float uz = ph[3] * qz + qw * ph[2] + (ph[0] * qy - ph[1] * qx);
+    const float uw = ph[3] * qw - (ph[0] * qx + ph[1] * qy + ph[2] * qz);
+    const float on_raw = sqrtf(uw * uw + ux * ux + uy * uy + uz * uz);
+    // ---- backward
+    // (1) oq = (uw, ux, uy, uz) / max(|u|, eps)
+    float gw, gx, gy, gz;
+    if (on_raw >= eps) {
+        const float inv = 1.0f / on_raw;
+        const float ow = uw * inv, ox = ux * inv, oy = uy * inv, oz = uz * inv;
+        const float dt = v_oq[0] * ow + v_oq[1] * ox + v_oq[2] * oy + v_oq[3] * oz;
+        gw = (v_oq[0] - dt * ow) * inv; gx = (v_oq[1] - dt * ox) * inv;
+        gy = (v_oq[2] - dt * oy) * inv; gz = (v_oq[3] - dt * oz) * inv;
+    } else {
+        gw = v_oq[0] / eps; gx = v_oq[1] / eps; gy = v_oq[2] / eps; gz = v_oq[3] / eps;
+    }
+    // (2) quaternion product u = ph (x) q (xyzw), bilinear
+    float v_ph[4];
+    v_ph[0] = gx * qw - gy * qz + gz * qy - gw * qx;
+    v_ph[1] = gx * qz + gy * qw - gz * qx - gw * qy;
+    v_ph[2] = -gx * qy + gy * qx + gz * qw - gw * qz;
+    v_ph[3] = gx * qx + gy * qy + gz * qz + gw * qw;
+    const float v_qx = gx * ph[3] + gy * ph[2] - gz * ph[1] - gw * ph[0];
+    const float v_qy = -gx * ph[2] + gy * ph[3] + gz * ph[0] - gw * ph[1];
+    const float v_qz = gx * ph[1] - gy * ph[0] + gz * ph[3] - gw * ph[2];
+    const float v_qw = gx * ph[0] + gy * ph[1] + gz * ph[2] + gw * ph[3];
+    // (3) q = xyzw(q_hat), q_hat = q_raw / max(|q_raw|, eps)
+    {
+        const float v_qh[4] = {v_qw, v_qx, v_qy, v_qz};
+        if (qn >= eps) {
+            const float dt = v_qh[0] * qh[0] + v_qh[1] * qh[1] + v_qh[2] * qh[2] + v_qh[3] * qh[3];
+            const float inv = 1.0f / qn;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) grad[12 + j] = (v_qh[j] - dt * qh[j]) * inv;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) grad[12 + j] = v_qh[j] / eps;
+        }
+    }
+    // (4) ph = p / |p|
+    float v_p[4];
+    {
+        const float dt = v_ph[0] * ph[0] + v_ph[1] * ph[1] + v_ph[2] * ph[2] + v_ph[3] * ph[3];
+        const float inv = 1.0f / pn;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v_p[j] = (v_ph[j] - dt * ph[j]) * inv;
+    }
+    // (5) p is linear in the entries of R = [x y z]
+    float v_x[3] = {0.f, 0.f, 0.f}, v_y[3] = {0.f, 0.f, 0.f}, v_z[3] = {0.f, 0.f, 0.f};
+    if (choice == 3) {
+        v_y[2] += v_p[0]; v_z[1] -= v_p[0]; v_z[0] += v_p[1]; v_x[2] -= v_p[1]; v_x[1] += v_p[2]; v_y[0] -= v_p[2];
+        v_x[0] += v_p[3]; v_y[1] += v_p[3]; v_z[2] += v_p[3];
+    } else if (choice == 0) {
+        v_x[0] += v_p[0]; v_y[1] -= v_p[0]; v_z[2] -= v_p[0]; v_x[1] += v_p[1]; v_y[0] += v_p[1];
+        v_x[2] += v_p[2]; v_z[0] += v_p[2]; v_y[2] += v_p[3]; v_z[1] -= v_p[3];
+    } else if (choice == 1) {
+        v_x[0] -= v_p[1]; v_y[1] += v_p[1]; v_z[2] -= v_p[1]; v_y[2] += v_p[2]; v_z[1] += v_p[2];
+        v_y[0] += v_p[0]; v_x[1] += v_p[0]; v_z[0] += v_p[3]; v_x[2] -= v_p[3];
+    } else {
+        v_x[0] -= v_p[2]; v_y[1] -= v_p[2]; v_z[2] += v_p[2]; v_z[0] += v_p[0]; v_x[2] += v_p[0];
+        v_z[1] += v_p[1]; v_y[2] += v_p[1]; v_x[1] += v_p[3]; v_y[0] -= v_p[3];
+    }
+    // (6) om = x mu0 + y mu1 + z mu2 + tl
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        grad[i] = v_om[i];
+        v_x[i] += v_om[i] * mu[0];
+        v_y[i] += v_om[i] * mu[1];
+        v_z[i] += v_om[i] * mu[2];
+    }
+    grad[9] = x[0] * v_om[0] + x[1] * v_om[1] + x[2] * v_om[2];
+    grad[10] = y[0] * v_om[0] + y[1] * v_om[1] + y[2] * v_om[2];
+    grad[11] = z[0] * v_om[0] + z[1] * v_om[1] + z[2] * v_om[2];
+    // (7) z = x cross y:  v_x += y cross v_z,  v_y += v_z cross x
+    v_x[0] += y[1] * v_z[2] - y[2] * v_z[1];
+    v_x[1] += y[2] * v_z[0] - y[0] * v_z[2];
+    v_x[2] += y[0] * v_z[1] - y[1] * v_z[0];
+    v_y[0] += v_z[1] * x[2] - v_z[2] * x[1];
+    v_y[1] += v_z[2] * x[0] - v_z[0] * x[2];
+    v_y[2] += v_z[0] * x[1] - v_z[1] * x[0];
+    // (8) y = yp / max(|yp|, eps)
+    float v_yp[3];
+    if (yn_raw >= eps) {
+        const float dt = v_y[0] * y[0] + v_y[1] * y[1] + v_y[2] * y[2];
+        const float inv = 1.0f / yn_raw;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v_yp[i] = (v_y[i] - dt * y[i]) * inv;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v_yp[i] = v_y[i] / eps;
+    }
+    // (9) yp = b - (b.x) x
+    {
+        const float dt = v_yp[0] * x[0] + v_yp[1] * x[1] + v_yp[2] * x[2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            grad[6 + i] = v_yp[i] - dt * x[i];
+            v_x[i] += -bx * v_yp[i] - dt * b[i];
+        }
+    }
+    // (10) x = a / max(|a|, eps)
+    if (an_raw >= eps) {
+        const float dt = v_x[0] * x[0] + v_x[1] * x[1] + v_x[2] * x[2];
+        const float inv = 1.0f / an_raw;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grad[3 + i] = (v_x[i] - dt * x[i]) * inv;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grad[3 + i] = v_x[i] / eps;
+    }
+}
+
 }  // namespace d4

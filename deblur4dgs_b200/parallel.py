@@ -299,16 +299,20 @@ def combine_band_units(imgs: Tensor, alphas: Tensor, subs: Sequence[int], bands:
 def render_frame_banded(times: Tensor, RTs: Optional[Tensor], height: int, render_units, ref_quirk: bool = True, group=None):
     """Strong scaling, 2-D partition: this rank renders N (sub-exposure, row band) units of ONE frame.
 
-    ``render_units(times_u [U], RTs_u [U,3,4] | None, row0 i32 [U], band_h) -> (imgs [U,1,band_h,W,D], alphas
-    [U,1,band_h,W,1])`` is the single-GPU path with row windows (``scene.render_subexposures(..., row_windows=(row0,
-    band_h), combine=False)``).  Returns the combined image [1,H,W,D] and alpha [1,H,W,1], replicated on every rank."""
+    ``render_units(times_d [S], RTs_d [S,3,4] | None, camera_of i64 [U], row0 i32 [U], band_h) -> (imgs
+    [U,1,band_h,W,D], alphas [U,1,band_h,W,1])`` is the single-GPU path with row windows: S distinct sub-exposures
+    are deformed, unit u shows sub-exposure ``camera_of[u]`` of them through the rows ``[row0[u], row0[u] + band_h)``
+    (``scene.render_subexposures(..., camera_of=..., row_windows=(row0, band_h), combine=False)``).  Returns the
+    combined image [1,H,W,D] and alpha [1,H,W,1], replicated on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     N = times.shape[0]
     band_h, n_bands = band_layout(height, world)
     units = band_units(N, rank, world)
     subs, bands = [u[0] for u in units], [u[1] for u in units]
-    idx = torch.as_tensor(subs, dtype=torch.long, device=times.device)
+    distinct = sorted(set(subs))
+    idx = torch.as_tensor(distinct, dtype=torch.long, device=times.device)
+    camera_of = torch.as_tensor([distinct.index(s) for s in subs], dtype=torch.long, device=times.device)
     row0 = torch.as_tensor([b * band_h for b in bands], dtype=torch.int32, device=times.device)
-    imgs, alphas = render_units(times[idx], None if RTs is None else RTs[idx], row0, band_h)
+    imgs, alphas = render_units(times[idx], None if RTs is None else RTs[idx], camera_of, row0, band_h)
     return combine_band_units(imgs, alphas, subs, bands, N, n_bands, height, ref_quirk, group)

@@ -87,10 +87,13 @@ def render_subexposures(
     combine: bool = True,
     ref_quirk: bool = True,
     capacity=None,  # rendering.RenderCapacity: sync-free tile binning (no device -> host read-back in the step)
-    row_windows=None,  # (row0 i32 [N], window_height): sub-exposure n renders that row band only (parallel.py)
+    row_windows=None,  # (row0 i32 [C], window_height): camera c renders that row band only (parallel.py)
+    camera_of=None,  # LongTensor [C]: camera c shows sub-exposure camera_of[c] of times / RTs (several row bands of one)
 ) -> Dict[str, Tensor]:
-    N = times.reshape(-1).shape[0]
     means, quats = deform_subexposures(fg_means, fg_quats, motion_coefs, bg_means, bg_quats, rots, transls, times, RTs)
+    if camera_of is not None:  # the deformation runs once per DISTINCT sub-exposure
+        means, quats = means.index_select(0, camera_of), quats.index_select(0, camera_of)
+    N = means.shape[0]
     bg = None if backgrounds is None else backgrounds.expand(N, -1)
     imgs, alphas, meta = rasterization(means=means, quats=quats, scales=scales, opacities=opacities, colors=colors,
                                        backgrounds=bg, viewmats=w2c, Ks=K, width=width, height=height, packed=False,

@@ -84,6 +84,14 @@ void hh_deform_point_vjp(const float *bl, const float *mu, const float *q, const
     }
 }
 
+// the hand-derived reverse-mode VJP of the same function (what the backward kernels run)
+void hh_deform_point_vjp_rev(const float *bl, const float *mu, const float *q, const float *vm, const float *vq, int n,
+                             float *grad, float *om) {
+    for (int i = 0; i < n; ++i)
+        deform_point_vjp(bl + 9 * i, bl + 9 * i + 3, mu + 3 * i, q + 4 * i, vm + 3 * i, vq + 4 * i, om + 3 * i,
+                         grad + 16 * i);
+}
+
 // camera interpolation (row a7): forward and dual-number VJP for sub-exposure parameter u
 void hh_camera_interp(const float *start6, const float *end6, const float *us, int n, float *Rt) {
     for (int i = 0; i < n; ++i) camera_interp_one<float>(start6, end6, us[i], Rt + 12 * i);

@@ -990,10 +990,12 @@ def test_row_window_bands_equal_full_render():
     imgs, alphas, subs, bands = [], [], [], []
     for rank in range(world):  # what every rank of a 4-rank job would render
         units = band_units(N, rank, world)
-        idx = torch.as_tensor([u[0] for u in units], device=DEV)
+        distinct = sorted({u[0] for u in units})  # deformed once each; several band cameras may show the same one
+        idx = torch.as_tensor(distinct, device=DEV)
+        camera_of = torch.as_tensor([distinct.index(u[0]) for u in units], device=DEV)
         row0 = torch.as_tensor([u[1] * band_h for u in units], dtype=torch.int32, device=DEV)
         ou = render_subexposures(*args_of(p1, c1), s.times[idx], s.RTs[idx], scales, opac, c1, s.w2c, s.K, W, H,
-                                 backgrounds=bg, combine=False, row_windows=(row0, band_h))
+                                 backgrounds=bg, combine=False, row_windows=(row0, band_h), camera_of=camera_of)
         assert ou["exposure_imgs"].shape == (N, 1, band_h, W, 17)
         imgs.append(ou["exposure_imgs"]); alphas.append(ou["exposure_alphas"])
         subs += [u[0] for u in units]; bands += [u[1] for u in units]
