@@ -182,6 +182,8 @@ def run_reference_arm(args):
 def workload_config(args, sc):
     d0 = 4 + sc.extra_channels.shape[1]
     name = args.config if not getattr(args, "checkpoint", None) else f"checkpoint {os.path.basename(args.checkpoint)}"
+    if getattr(args, "scale_mult", 1.0) != 1.0:
+        name += f" (Gaussian scales x{args.scale_mult})"
     return {"workload": f"{name}: {sc.width}x{sc.height}, G={sc.G} (fg {sc.num_fg}), K={sc.rots.shape[0]}, "
                         f"N={sc.N} sub-exposures, D={d0 + 1} channels (RGB+ED), fwd+bwd",
             "shard": args.shard, "l2": "per-step working set (N x H x W x D image stack, 564 MB at c3) exceeds the 126 MB L2"}
@@ -203,6 +205,8 @@ def main():
                          "measured as the 'strong' object of every multi-GPU frames run); subexposures: round-robin "
                          "sub-exposures (strong, unbalanced for N=9 on 8 ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scale-mult", type=float, default=1.0, help="multiplier on the Gaussian scales of the synthetic "
+                                                                   "scene (BASELINE configs[4]: sweep 0.5 / 1 / 2)")
     ap.add_argument("--sync", action="store_true", help="gsplat-style binning with its device->host read-back every step "
                                                         "(default: sync-free capacity mode, rendering.RenderCapacity)")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg of the resident measurement")
@@ -244,7 +248,7 @@ def main():
         sc_cpu, _ = load_checkpoint(args.checkpoint, W, H, frame=args.frame, N=N)
         G, K = sc_cpu.G, sc_cpu.rots.shape[0]
     else:
-        sc_cpu = make_config(args.config, seed=seed + (rank if args.shard == "frames" else 0))
+        sc_cpu = make_config(args.config, seed=seed + (rank if args.shard == "frames" else 0), scale_mult=args.scale_mult)
     D0 = 4 + sc_cpu.extra_channels.shape[1]  # rgb + fg mask + track channels
     host = {k: v.pin_memory() for k, v in sc_cpu.tensors().items()}
     sc = sc_cpu.to(dev)
@@ -460,7 +464,8 @@ def main():
     # the frame's N x world (sub-exposure, tile-row band) units over the ranks, image / extrema / gradient all-reduce
     strong = None
     if world > 1 and args.shard == "frames":
-        sc_frame = make_config(args.config, seed=seed).to(dev) if not args.checkpoint else sc  # the SAME frame on every rank
+        # the SAME frame on every rank
+        sc_frame = make_config(args.config, seed=seed, scale_mult=args.scale_mult).to(dev) if not args.checkpoint else sc
         for _ in range(max(3, args.warmup)):
             step(sc_frame, shard="bands")
         torch.cuda.synchronize()

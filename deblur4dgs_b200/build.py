@@ -32,6 +32,7 @@ UNITS = {
     "deform.cu": [],
     "combine.cu": [],
     "band_combine.cu": [],
+    "correlation.cu": [],
     "camera.cu": [],
     "assemble.cu": [],
 }

@@ -283,8 +283,8 @@ tile_offsets_kernel(const int64_t *__restrict__ ids, int64_t n, int n_tiles, int
 //       (depth bits << 32 | flatten id) with a bitonic network and writes the final lists.
 // ~20-28 B of HBM traffic per intersection instead of 6 passes x 36 B.  The result is bit-identical
 // to the stable radix sort: ties in depth are ordered by flatten id, which is emission order.
-constexpr int kTileSortMax = 4096;      // segment capacity of the shared-memory sort without opt-in (32 KB of keys)
-constexpr int kTileSortMaxCap = 16384;  // with the > 48 KB dynamic shared memory opt-in (128 KB of keys)
+constexpr int kTileSortMaxCap = 16384;  // segment capacity of the shared-memory sort (128 KB of keys; > 4096 keys
+                                        // need the dynamic shared memory opt-in and leave one CTA per SM)
 
 __device__ __forceinline__ void tile_rect_dev(float m2x, float m2y, int32_t radius, int tile_size, int tile_w,
                                               int tile_h, int &x0, int &y0, int &x1, int &y1) {
@@ -489,7 +489,7 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
 
 using namespace d4;
 
-extern "C" int d4_tile_sort_capacity(void) { return kTileSortMax; }
+extern "C" int d4_tile_sort_capacity(void) { return kTileSortMaxCap; }
 
 extern "C" int d4_tile_count(const float *means2d, const int32_t *radii, int C, int G, int tile_size, int tile_w,
                              int tile_h, int32_t *tile_counts, d4_stream_t stream) {
@@ -571,8 +571,8 @@ extern "C" int d4_tile_sort_pack(const uint64_t *bucket_keys, const int32_t *til
                                  const float *depths, int G, int tile_size, void *recs, int32_t *rec_counts,
                                  d4_stream_t stream) {
     D4_CHECK_ARG(C >= 1 && tile_w >= 1 && tile_h >= 1 && n_isects >= 0, "d4_tile_sort_pack: bad arguments");
-    D4_CHECK_ARG(max_count <= kTileSortMax, "d4_tile_sort_pack: a tile holds %d intersections, capacity is %d "
-                                            "(use d4_isect_emit + d4_sort_pairs_u64 + d4_isect_pack)", max_count, kTileSortMax);
+    D4_CHECK_ARG(max_count <= kTileSortMaxCap, "d4_tile_sort_pack: a tile holds %d intersections, capacity is %d "
+                                               "(use d4_isect_emit + d4_sort_pairs_u64 + d4_isect_pack)", max_count, kTileSortMaxCap);
     if (int rc = check_pack("d4_tile_sort_pack", means2d, conics, opacities, G, tile_size, (float4 *)recs, rec_counts)) return rc;
     D4_CHECK_ARG(tile_offsets, "d4_tile_sort_pack: null pointer");
     const int64_t n_seg = (int64_t)C * tile_w * tile_h;
@@ -606,8 +606,8 @@ extern "C" int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_off
                             int tile_w, int tile_h, int max_count, int64_t *isect_ids, int32_t *flatten_ids,
                             d4_stream_t stream) {
     D4_CHECK_ARG(C >= 1 && tile_w >= 1 && tile_h >= 1 && n_isects >= 0, "d4_tile_sort: bad arguments");
-    D4_CHECK_ARG(max_count <= kTileSortMax, "d4_tile_sort: a tile holds %d intersections, capacity is %d "
-                                            "(use d4_isect_emit + d4_sort_pairs_u64)", max_count, kTileSortMax);
+    D4_CHECK_ARG(max_count <= kTileSortMaxCap, "d4_tile_sort: a tile holds %d intersections, capacity is %d "
+                                               "(use d4_isect_emit + d4_sort_pairs_u64)", max_count, kTileSortMaxCap);
     if (n_isects == 0) return 0;
     D4_CHECK_ARG(bucket_keys && tile_offsets && isect_ids && flatten_ids, "d4_tile_sort: null pointer");
     return launch_tile_sort("d4_tile_sort", bucket_keys, tile_offsets, n_isects, nullptr, n_isects, max_count, nullptr, C,

@@ -354,7 +354,8 @@ def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, ti
                  tile_height, ptr(offsets), ptr(flatten_ids), n, ptr(recs), ptr(rec_counts), st)
         return isect_ids, flatten_ids, offsets, recs, rec_counts
 
-    if capacity is not None and capacity.ready and pack is not None and method != "radix":
+    if (capacity is not None and capacity.ready and pack is not None and method != "radix"
+            and capacity.seen_tile <= _cabi.lib().d4_tile_sort_capacity_max()):
         # ---- capacity mode: no device -> host read-back; one zero-filled int workspace (counts | cursors | stats)
         capacity.poll()
         lib = _cabi.lib()

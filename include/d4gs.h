@@ -323,6 +323,15 @@ int d4_densify_stats(const float *v_means2d, const int32_t *radii, int N, int G,
                      float inv_max_wh, float *grad_norm_acc, int64_t *vis_count, float *max_radii,
                      d4_stream_t stream);
 
+/* ---- f4 ("next" row): PWC-Net cost volume of the AlignedLoss front-end -----------------------------------
+ * replaces _FunctionCorrelation.forward (flow3d/models/external/pwcnet/correlation/correlation.py:281-331) and its
+ * CuPy kernels kernel_Correlation_rearrange (:8-33, twice) + kernel_Correlation_updateOutput (:35-103), reached from
+ * flow3d/models/pwcnet.py:179,187.  first / second [B,C,H,W] (NCHW, contiguous) -> out [B,81,H,W]:
+ *   out[b, (dy+4)*9 + (dx+4), y, x] = (1/C) sum_c first[b,c,y,x] * second[b,c,y+dy,x+dx],  dx, dy in [-4,4],
+ * zero outside the image.  Forward only: the reference evaluates PWC-Net under no_grad (loss_utils.py:171-172).   */
+int d4_correlation_fwd(const float *first, const float *second, int B, int C, int H, int W, float *out,
+                       d4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1038,3 +1038,28 @@ def test_band_combine_kernels_equal_host_expressions():
                 res.append([t.detach().cpu() for t in (out, oa, a.grad, b.grad)])
             for x, y in zip(*res):
                 assert torch.allclose(x, y, atol=1e-6), (rank, quirk)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 45, 80), (1, 196, 6, 10), (1, 64, 23, 40), (3, 5, 9, 33), (1, 128, 12, 20)])
+def test_correlation_f4_vs_oracle(B, C, H, W):
+    """Row f4: the PWC-Net cost volume (flow3d/models/external/pwcnet/correlation/correlation.py:8-103) against the
+    numpy restatement of the reference's CuPy kernels.  The kernel sums the C products per output in channel order,
+    the reference in 32 interleaved lanes: agreement to fp32 round-off of a C-term dot product, held to 2e-6 of the
+    tensor scale (measured <= 4e-7)."""
+    from deblur4dgs_b200._cabi import D4Error
+    from deblur4dgs_b200.correlation import FunctionCorrelation, ModuleCorrelation
+    from oracle import correlation as ocorr
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    a, b = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    ref = ocorr.correlation(a.numpy(), b.numpy())
+    with torch.no_grad():
+        got = FunctionCorrelation(a.to(DEV), b.to(DEV))
+        got2 = ModuleCorrelation()(a.to(DEV), b.to(DEV))
+    assert got.shape == (B, 81, H, W) and torch.equal(got, got2)
+    e = scale_err(got.cpu().numpy(), ref)
+    report(test=f"correlation_{B}x{C}x{H}x{W}", kind="correlation", scale_err=e)
+    assert e <= 2e-6, e
+    with pytest.raises(D4Error):
+        FunctionCorrelation(a.to(DEV).requires_grad_(True), b.to(DEV))
+    with pytest.raises(D4Error):
+        FunctionCorrelation(a, b)
