@@ -32,10 +32,10 @@ PROTOTYPES = {
     "d4_sort_pairs_u64": (c_int, [P, P, P, P, L, I, I, P, c_size_t, POINTER(c_int), P]),
     "d4_tile_sort_capacity": (c_int, []),
     "d4_tile_count": (c_int, [P, P, I, I, I, I, I, P, P]),
-    "d4_bucket_emit": (c_int, [P, P, P, I, I, I, I, I, P, P, P, L, P]),
+    "d4_bucket_emit": (c_int, [P, P, P, I, I, I, I, I, P, P, P, L, I, P]),
     "d4_tile_sort_capacity_max": (c_int, []),
     "d4_scan_counts": (c_int, [P, L, P, P, P, c_size_t, P]),
-    "d4_tile_sort_pack_cap": (c_int, [P, P, P, L, I, I, I, I, P, P, P, P, P, P, I, I, P, P, P, P]),
+    "d4_tile_sort_pack_cap": (c_int, [P, P, P, L, I, I, I, I, P, P, P, P, P, P, I, I, P, P, P, I, P]),
     "d4_tile_sort": (c_int, [P, P, L, I, I, I, I, P, P, P]),
     "d4_tile_offsets": (c_int, [P, L, I, I, I, P, P]),
     "d4_blend_fwd": (c_int, [P, P, P, P, L, P, P, I, I, I, I, I, I, I, I, P, P, L, I, P, P, P, P, P, P]),

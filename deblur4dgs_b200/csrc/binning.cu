@@ -329,7 +329,9 @@ __global__ void __launch_bounds__(256)
 bucket_emit_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
                    const float *__restrict__ depths, int C, int G, int tile_size, int tile_w, int tile_h,
                    const int32_t *__restrict__ tile_offsets, int32_t *__restrict__ cursors,
-                   uint64_t *__restrict__ bucket_keys, int64_t capacity) {
+                   uint64_t *__restrict__ bucket_keys, int64_t capacity, int bucket_stride) {
+    // bucket_stride > 0: fixed-stride buckets (tile t owns bucket_keys[t * bucket_stride ...], no offsets needed: the
+    // count pass and the scan before the emit are skipped; `cursors` doubles as the per-tile counts)
     const int64_t tg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t idx = tg / kLanesPerGauss;
     const int sub = (int)(tg - idx * kLanesPerGauss);
@@ -345,8 +347,13 @@ bucket_emit_kernel(const float *__restrict__ means2d, const int32_t *__restrict_
     for (int q = sub; q < n; q += kLanesPerGauss) {
         const int i = q / wx, j = q - i * wx;
         const int64_t t = cbase + (y0 + i) * tile_w + x0 + j;
-        const int32_t pos = tile_offsets[t] + atomicAdd(cursors + t, 1);
-        if (pos < capacity) bucket_keys[pos] = key;  // beyond the caller's capacity: dropped, the overflow is flagged by the sort
+        const int32_t slot = atomicAdd(cursors + t, 1);
+        if (bucket_stride > 0) {
+            if (slot < bucket_stride) bucket_keys[t * bucket_stride + slot] = key;
+        } else {
+            const int32_t pos = tile_offsets[t] + slot;
+            if (pos < capacity) bucket_keys[pos] = key;  // beyond the caller's capacity: dropped, the overflow is flagged by the sort
+        }
     }
 }
 
@@ -418,7 +425,8 @@ __global__ void __launch_bounds__(256)
 tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__restrict__ tile_offsets, int64_t n_isects,
                  const int64_t *__restrict__ n_isects_dev, int64_t capacity, int sort_capacity,
                  int64_t *__restrict__ overflow, int64_t n_segments, int n_tiles, int tile_n_bits,
-                 int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids, PackArgs pack) {
+                 int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids, PackArgs pack,
+                 const int32_t *__restrict__ bucket_counts, int bucket_stride) {
     extern __shared__ uint64_t s_keys[];
     __shared__ int32_t s_warp[8];
     const int64_t seg = blockIdx.x;
@@ -428,7 +436,11 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
     if (n_isects_dev) n_isects = *n_isects_dev;
     const int64_t start64 = tile_offsets[seg];
     const int64_t end64 = (seg == n_segments - 1) ? n_isects : (int64_t)tile_offsets[seg + 1];
-    const bool fits = end64 <= capacity && end64 - start64 <= sort_capacity;
+    // fixed-stride buckets: the unsorted keys of the segment sit at bucket_keys[seg * bucket_stride ...]
+    const bool fits = end64 <= capacity && end64 - start64 <= sort_capacity &&
+                      (bucket_stride == 0 || end64 - start64 <= bucket_stride);
+    const uint64_t *src_keys = bucket_stride > 0 ? bucket_keys + seg * (int64_t)bucket_stride : bucket_keys + start64;
+    (void)bucket_counts;
     if (!fits && overflow && threadIdx.x == 0) *overflow = 1;
     const int32_t start = (int32_t)start64;
     const int n = fits ? (int)(end64 - start64) : 0;
@@ -438,7 +450,7 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
     }
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[i] = i < n ? bucket_keys[start + i] : ~0ull;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[i] = i < n ? src_keys[i] : ~0ull;
     __syncthreads();
     // Bitonic network.  Stages with partner distance j <= 32 only exchange within aligned 64-key chunks: chunk q is
     // owned by warp q % 8 for the whole sort, so those stages need a warp barrier only.  Block barriers remain
@@ -504,13 +516,13 @@ extern "C" int d4_tile_count(const float *means2d, const int32_t *radii, int C, 
 
 extern "C" int d4_bucket_emit(const float *means2d, const int32_t *radii, const float *depths, int C, int G,
                               int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets, int32_t *cursors,
-                              uint64_t *bucket_keys, int64_t capacity, d4_stream_t stream) {
-    D4_CHECK_ARG(capacity >= 0 && capacity < (1LL << 31), "d4_bucket_emit: bad capacity");
+                              uint64_t *bucket_keys, int64_t capacity, int bucket_stride, d4_stream_t stream) {
+    D4_CHECK_ARG(capacity >= 0 && capacity < (1LL << 31) && bucket_stride >= 0, "d4_bucket_emit: bad capacity");
     D4_CHECK_ARG(C >= 1 && G >= 0 && (int64_t)C * G < (1LL << 32), "d4_bucket_emit: bad sizes");
     if (G == 0) return 0;
-    D4_CHECK_ARG(means2d && radii && depths && tile_offsets && cursors && bucket_keys, "d4_bucket_emit: null pointer");
+    D4_CHECK_ARG(means2d && radii && depths && (tile_offsets || bucket_stride > 0) && cursors && bucket_keys, "d4_bucket_emit: null pointer");
     bucket_emit_kernel<<<cdiv((int64_t)C * G * kLanesPerGauss, 256), 256, 0, as_stream(stream)>>>(
-        means2d, radii, depths, C, G, tile_size, tile_w, tile_h, tile_offsets, cursors, bucket_keys, capacity);
+        means2d, radii, depths, C, G, tile_size, tile_w, tile_h, tile_offsets, cursors, bucket_keys, capacity, bucket_stride);
     D4_CHECK_LAUNCH("d4_bucket_emit");
     return 0;
 }
@@ -548,7 +560,7 @@ extern "C" size_t d4_slab_hit_words(int64_t n_isects, int64_t n_segments) { retu
 static int launch_tile_sort(const char *name, const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects,
                             const int64_t *n_isects_dev, int64_t capacity, int sort_capacity, int64_t *overflow, int C,
                             int tile_w, int tile_h, int64_t *isect_ids, int32_t *flatten_ids, const PackArgs &p,
-                            cudaStream_t st) {
+                            cudaStream_t st, int bucket_stride = 0) {
     int n_pad = 1;
     while (n_pad < sort_capacity) n_pad <<= 1;
     const size_t smem = sizeof(uint64_t) * (size_t)n_pad;
@@ -560,7 +572,7 @@ static int launch_tile_sort(const char *name, const uint64_t *bucket_keys, const
     const int64_t n_seg = (int64_t)C * tile_w * tile_h;
     tile_sort_kernel<<<(unsigned)n_seg, 256, smem, st>>>(bucket_keys, tile_offsets, n_isects, n_isects_dev, capacity, n_pad,
                                                         overflow, n_seg, tile_w * tile_h, d4_tile_n_bits(tile_w * tile_h),
-                                                        isect_ids, flatten_ids, p);
+                                                        isect_ids, flatten_ids, p, nullptr, bucket_stride);
     D4_CHECK_LAUNCH(name);
     return 0;
 }
@@ -590,7 +602,7 @@ extern "C" int d4_tile_sort_pack_cap(const uint64_t *bucket_keys, const int32_t 
                                      int64_t capacity, int sort_capacity, int C, int tile_w, int tile_h,
                                      int64_t *isect_ids, int32_t *flatten_ids, const float *means2d, const float *conics,
                                      const float *opacities, const float *depths, int G, int tile_size, void *recs,
-                                     int32_t *rec_counts, int64_t *overflow, d4_stream_t stream) {
+                                     int32_t *rec_counts, int64_t *overflow, int bucket_stride, d4_stream_t stream) {
     D4_CHECK_ARG(C >= 1 && tile_w >= 1 && tile_h >= 1 && capacity >= 1 && capacity < (1LL << 31) && sort_capacity >= 1 &&
                      sort_capacity <= kTileSortMaxCap,
                  "d4_tile_sort_pack_cap: bad arguments (sort capacity <= %d)", kTileSortMaxCap);
@@ -598,8 +610,9 @@ extern "C" int d4_tile_sort_pack_cap(const uint64_t *bucket_keys, const int32_t 
     D4_CHECK_ARG(bucket_keys && tile_offsets && bin_stats && isect_ids && flatten_ids && overflow,
                  "d4_tile_sort_pack_cap: null pointer");
     PackArgs p{means2d, conics, opacities, depths, G, tile_w, tile_size, (float4 *)recs, rec_counts};
+    D4_CHECK_ARG(bucket_stride >= 0, "d4_tile_sort_pack_cap: bad bucket stride");
     return launch_tile_sort("d4_tile_sort_pack_cap", bucket_keys, tile_offsets, 0, bin_stats, capacity, sort_capacity, overflow,
-                            C, tile_w, tile_h, isect_ids, flatten_ids, p, as_stream(stream));
+                            C, tile_w, tile_h, isect_ids, flatten_ids, p, as_stream(stream), bucket_stride);
 }
 
 extern "C" int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,

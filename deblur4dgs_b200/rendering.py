@@ -360,26 +360,28 @@ def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, ti
         capacity.poll()
         lib = _cabi.lib()
         cap = capacity.n_isects
-        izero = torch.zeros((2 * n_seg + 8,), dtype=torch.int32, device=dev)
+        # fixed-stride buckets (tile t owns keys[t * stride ...]): the emit counts while it writes, so the separate
+        # count pass is gone -- emit -> scan of the counts (== isect_offsets) -> per-tile sort into the compact lists
+        stride = capacity.sort_cap
+        izero = torch.zeros((n_seg + 8,), dtype=torch.int32, device=dev)
         _cabi.count_fill()
-        counts, cursors = izero[:n_seg], izero[n_seg:2 * n_seg]
-        stats = izero[2 * n_seg:2 * n_seg + 8].view(torch.int64)  # n_isects, max per tile, overflow, -
-        call("d4_tile_count", ptr(means2d), ptr(radii), C, G, tile_size, tile_width, tile_height, ptr(counts), st)
+        counts = izero[:n_seg]
+        stats = izero[n_seg + (n_seg & 1):n_seg + (n_seg & 1) + 6].view(torch.int64)  # n_isects, max per tile, overflow
+        keys = torch.empty((n_seg * stride,), dtype=torch.int64, device=dev)
+        call("d4_bucket_emit", ptr(means2d), ptr(radii), ptr(depths), C, G, tile_size, tile_width, tile_height,
+             None, ptr(counts), ptr(keys), cap, stride, st)
         offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
         ws_bytes = lib.d4_scan_workspace_bytes(n_seg)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         call("d4_scan_counts", ptr(counts), n_seg, ptr(offsets), ptr(stats), ptr(ws), ws_bytes, st)
         isect_ids = torch.empty((cap,), dtype=torch.int64, device=dev)
         flatten_ids = torch.empty((cap,), dtype=torch.int32, device=dev)
-        keys = torch.empty((cap,), dtype=torch.int64, device=dev)
-        call("d4_bucket_emit", ptr(means2d), ptr(radii), ptr(depths), C, G, tile_size, tile_width, tile_height,
-             ptr(offsets), ptr(cursors), ptr(keys), cap, st)
         conics, opacities, bdepths = pack
         recs = torch.empty((cap, 8), dtype=torch.float32, device=dev)
         rec_counts = torch.empty((n_seg,), dtype=torch.int32, device=dev)
         call("d4_tile_sort_pack_cap", ptr(keys), ptr(offsets), ptr(stats), cap, capacity.sort_cap, C, tile_width,
              tile_height, ptr(isect_ids), ptr(flatten_ids), ptr(means2d), ptr(conics), ptr(opacities), ptr(bdepths), G,
-             tile_size, ptr(recs), ptr(rec_counts), ptr(stats[2:]), st)
+             tile_size, ptr(recs), ptr(rec_counts), ptr(stats[2:]), stride, st)
         capacity.record(stats)
         return isect_ids, flatten_ids, offsets, recs, rec_counts
 
@@ -412,7 +414,7 @@ def bin_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, ti
         return packed(isect_ids, flatten_ids, offsets)
     keys = torch.empty((n_isects,), dtype=torch.int64, device=dev)
     call("d4_bucket_emit", ptr(means2d), ptr(radii), ptr(depths), C, G, tile_size, tile_width, tile_height,
-         ptr(offsets), ptr(cursors), ptr(keys), n_isects, st)
+         ptr(offsets), ptr(cursors), ptr(keys), n_isects, 0, st)
     if pack is None:
         call("d4_tile_sort", ptr(keys), ptr(offsets), n_isects, C, tile_width, tile_height, max_count, ptr(isect_ids),
              ptr(flatten_ids), st)

@@ -107,6 +107,8 @@ int d4_tile_count(const float *means2d, const int32_t *radii, int C, int G, int 
 int d4_bucket_emit(const float *means2d, const int32_t *radii, const float *depths, int C, int G,
                    int tile_size, int tile_w, int tile_h, const int32_t *tile_offsets, int32_t *cursors,
                    uint64_t *bucket_keys, int64_t capacity /* entries of bucket_keys; writes beyond are dropped */,
+                   int bucket_stride /* > 0: fixed-stride buckets, tile t at bucket_keys[t * bucket_stride]; tile_offsets
+                                        may be NULL and `cursors` ends up holding the per-tile counts */,
                    d4_stream_t stream);
 int d4_tile_sort(const uint64_t *bucket_keys, const int32_t *tile_offsets, int64_t n_isects, int C,
                  int tile_w, int tile_h, int max_count, int64_t *isect_ids, int32_t *flatten_ids,
@@ -176,7 +178,9 @@ int d4_tile_sort_pack(const uint64_t *bucket_keys, const int32_t *tile_offsets, 
  * the count from bin_stats[0] on the device; all per-intersection buffers hold `capacity` entries, the per-tile
  * shared-memory sort `sort_capacity` keys (<= d4_tile_sort_capacity_max()).  A tile that does not fit is left
  * without records and *overflow (device int64, caller zero-fills) is set to 1: the caller reads it whenever it
- * next synchronises and re-renders with a larger capacity.                                                   */
+ * next synchronises and re-renders with a larger capacity.  With fixed-stride buckets (bucket_stride > 0) the
+ * count pass disappears: d4_bucket_emit counts while it emits, d4_scan_counts turns the counts into offsets, and
+ * the sort reads tile t's keys from its bucket and writes the sorted lists compactly at tile_offsets[t].          */
 int d4_tile_sort_capacity_max(void);
 int d4_scan_counts(const int32_t *counts, int64_t n, int32_t *offsets, int64_t *stats, void *workspace,
                    size_t workspace_bytes, d4_stream_t stream);
@@ -184,7 +188,9 @@ int d4_tile_sort_pack_cap(const uint64_t *bucket_keys, const int32_t *tile_offse
                           int64_t capacity, int sort_capacity, int C, int tile_w, int tile_h,
                           int64_t *isect_ids, int32_t *flatten_ids, const float *means2d, const float *conics,
                           const float *opacities, const float *depths, int G, int tile_size, void *recs,
-                          int32_t *rec_counts, int64_t *overflow, d4_stream_t stream);
+                          int32_t *rec_counts, int64_t *overflow,
+                          int bucket_stride /* as d4_bucket_emit; 0 = compact buckets at tile_offsets */,
+                          d4_stream_t stream);
 /* u32 words of the hit_bits buffer below: ((n_isects >> 5) + n_segments + 1) * 8 */
 size_t d4_slab_hit_words(int64_t n_isects, int64_t n_segments);
 
