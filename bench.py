@@ -549,7 +549,7 @@ def main():
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "gpu_launches_per_step": launches_per_step,
             "gpu_launches_detail": {"libd4gs_kernels_per_step": own_launches_per_step,
-                                    "torch_zero_fills_per_step": fills_per_step,
+                                    "torch_fill_copy_kernels_per_step": fills_per_step,
                                     "host_syncs_per_step": 1 if cap is None else 0},
             "strong": strong,
             "graph": None if graph_ms is None else {"ms_per_step": graph_ms, "value": frames_per_step_global / (graph_ms * 1e-3),

@@ -93,7 +93,7 @@ PROFILE = None
 LAUNCHES = {"d4_deform_fwd": 2, "d4_deform_bwd": 2, "d4_exclusive_scan_i32": 2, "d4_scan_counts": 2}
 
 
-FILLS = 0  # torch-side zero-fill kernels issued by the op code (counted so that bench.py reports every launch)
+FILLS = 0  # torch-side kernels (zero-fills, one tiny copy) issued by the op code: counted so that bench.py reports every launch
 
 
 def count_fill(n: int = 1):

@@ -214,6 +214,7 @@ class _Projection(torch.autograd.Function):
         ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii, conics)
         ctx.cfg = (C, G, ms, qs, vs, ks, width, height, eps2d)
         ctx.mark_non_differentiable(radii, tiles_per_gauss)
+        ctx.set_materialize_grads(False)  # no zero-filled [C,G] "gradients" for the integer outputs
         return radii, means2d, depths, conics, tiles_per_gauss
 
     @staticmethod
@@ -500,6 +501,8 @@ class _BlendSlab(torch.autograd.Function):
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, isect_offsets, recs, rec_counts, width,
                 height, tile_size, normalize_depth):
         _check_cuda(means2d, conics, opacities, colors, recs)
+        if backgrounds is not None and not backgrounds.is_contiguous():
+            _cabi.count_fill()  # the [C,D0] background rows of an expand()ed view are materialised by a torch copy kernel
         colors, backgrounds = _f32c(colors), _f32c(backgrounds)
         C, G = means2d.shape[:2]
         D0 = colors.shape[-1]

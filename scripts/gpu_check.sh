@@ -12,13 +12,13 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | 
 echo "== bench"
 timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log
 if [ "$mode" = "full" ]; then
-  echo "== ncu launch list"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 200 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  echo "== ncu launch list (every kernel of 3 warm-up + 2 timed + 4 e2e steps)"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_bench.log 2>&1
   tail -2 gpurun_out/ncu_bench.log
-  echo "== ncu full capture of blend kernels"
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:blend_ -s 6 -c 4 \
-      -o gpurun_out/prof_blend -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+  echo "== ncu full capture of the blend kernels"
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:blend_ -s 6 -c 2 \
+      -o gpurun_out/r02_blend_final -f python scripts/ab_paths.py --config c3 --steps 1 --paths slab > gpurun_out/ncu_full.log 2>&1
   tail -2 gpurun_out/ncu_full.log
-  ls -la gpurun_out
+  ls -la gpurun_out | tail -5
 fi
