@@ -506,9 +506,11 @@ def main():
         ab = algorithmic_bytes(sc.G, sc.num_fg, K, Dtot, P, I_frame, tiles)
         peak, peak_src = peaks()
         dom = "d4_blend_bwd_slab"
-        dom_kernel = f"blend_bwd_slab_kernel<{D0}, 1>"
+        # which kernel d4_blend_bwd_slab launches: the tensor-core formulation serves the 16-colour records
+        variant = _cabi.lib().d4_blend_bwd_slab_default_variant() if D0 == 16 else 0
+        dom_kernel = f"blend_bwd_slab_tc_kernel<1, {int(variant == 2)}>" if variant else f"blend_bwd_slab_kernel<{D0}, 1>"
         dom_ms = kernel_ms.get(dom, float("nan"))
-        cap, cap_src = measured_capture(f"blend_bwd_slab_kernel<{D0}")
+        cap, cap_src = measured_capture(dom_kernel.split(",")[0])
         if args.config != "c3" or world != 1 or args.checkpoint:
             cap, cap_src = {}, None  # the capture is of the c3 single-GPU launch
         traffic = cap.get("dram_bytes_per_launch")

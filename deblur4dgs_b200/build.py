@@ -29,6 +29,7 @@ UNITS = {
     "blend_bwd_gp.cu": [],
     "blend_slab_fwd.cu": [],
     "blend_slab_bwd.cu": [],
+    "blend_slab_bwd_tc.cu": [],
     "deform.cu": [],
     "combine.cu": [],
     "band_combine.cu": [],

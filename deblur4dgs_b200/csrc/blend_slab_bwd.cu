@@ -439,6 +439,39 @@ int launch_blend_bwd_slab(int D0, bool depth, const SlabArgs &a, const float *ra
 
 using namespace d4;
 
+static int blend_bwd_slab_any(const char *name, int variant, const void *recs, const int32_t *tile_offsets,
+                              const int32_t *rec_counts, const float *colors, int64_t colors_cam_stride,
+                              const float *backgrounds, int C, int G, int D0, int with_depth, int width, int height,
+                              int tile_size, int tile_w, int tile_h, int normalize_depth, const float *render_alphas,
+                              const int32_t *last_ids, const float *acc_depth, const float *v_render_colors,
+                              const float *v_render_alphas, const uint32_t *hit_bits, float *v_means2d, float *v_conics,
+                              float *v_colors, float *v_opacities, float *v_depths, d4_stream_t stream) {
+    SlabArgs a{(const float4 *)recs, tile_offsets, rec_counts, colors, colors_cam_stride, backgrounds,
+               const_cast<uint32_t *>(hit_bits), C, G, width, height, tile_w, tile_h, normalize_depth};
+    if (int rc = check_slab_args(name, a, D0, tile_size)) return rc;
+    D4_CHECK_ARG(render_alphas && last_ids && v_render_colors && v_render_alphas && hit_bits && v_means2d && v_conics &&
+                     v_opacities && v_colors,
+                 "%s: null pointer", name);
+    D4_CHECK_ARG(!with_depth || v_depths, "%s: v_depths required with the depth channel", name);
+    D4_CHECK_ARG(!normalize_depth || (with_depth && acc_depth), "%s: normalize_depth needs the depth channel and acc_depth", name);
+    D4_CHECK_ARG(variant >= 0 && variant <= 2, "%s: variant must be 0 (fp32 pipe), 1 or 2 (tensor cores)", name);
+    int rc = -1;
+    if (variant > 0)  // served for the 16-colour records with 8-byte aligned gradient rows, otherwise falls through
+        rc = launch_blend_bwd_slab_tc(variant, D0, with_depth != 0, a, render_alphas, last_ids, acc_depth, v_render_colors,
+                                      v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_depths,
+                                      as_stream(stream));
+    if (rc < 0)
+        rc = launch_blend_bwd_slab(D0, with_depth != 0, a, render_alphas, last_ids, acc_depth, v_render_colors,
+                                   v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_depths,
+                                   as_stream(stream));
+    if (rc != 0) {
+        set_error("%s: %s", name, rc < 0 ? "channel count not built" : "kernel configuration failed");
+        return rc < 0 ? 2 : 1;
+    }
+    D4_CHECK_LAUNCH(name);
+    return 0;
+}
+
 extern "C" int d4_blend_bwd_slab(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
                                  const float *colors, int64_t colors_cam_stride, const float *backgrounds, int C, int G,
                                  int D0, int with_depth, int width, int height, int tile_size, int tile_w, int tile_h,
@@ -446,21 +479,24 @@ extern "C" int d4_blend_bwd_slab(const void *recs, const int32_t *tile_offsets, 
                                  const float *acc_depth, const float *v_render_colors, const float *v_render_alphas,
                                  const uint32_t *hit_bits, float *v_means2d, float *v_conics, float *v_colors,
                                  float *v_opacities, float *v_depths, d4_stream_t stream) {
-    SlabArgs a{(const float4 *)recs, tile_offsets, rec_counts, colors, colors_cam_stride, backgrounds,
-               const_cast<uint32_t *>(hit_bits), C, G, width, height, tile_w, tile_h, normalize_depth};
-    if (int rc = check_slab_args("d4_blend_bwd_slab", a, D0, tile_size)) return rc;
-    D4_CHECK_ARG(render_alphas && last_ids && v_render_colors && v_render_alphas && hit_bits && v_means2d && v_conics &&
-                     v_opacities && v_colors,
-                 "d4_blend_bwd_slab: null pointer");
-    D4_CHECK_ARG(!with_depth || v_depths, "d4_blend_bwd_slab: v_depths required with the depth channel");
-    D4_CHECK_ARG(!normalize_depth || (with_depth && acc_depth), "d4_blend_bwd_slab: normalize_depth needs the depth channel and acc_depth");
-    const int rc = launch_blend_bwd_slab(D0, with_depth != 0, a, render_alphas, last_ids, acc_depth, v_render_colors,
-                                         v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_depths,
-                                         as_stream(stream));
-    if (rc != 0) {
-        set_error("d4_blend_bwd_slab: %s", rc < 0 ? "channel count not built" : "kernel configuration failed");
-        return rc < 0 ? 2 : 1;
-    }
-    D4_CHECK_LAUNCH("d4_blend_bwd_slab");
-    return 0;
+    return blend_bwd_slab_any("d4_blend_bwd_slab", D4_BLEND_BWD_DEFAULT_VARIANT, recs, tile_offsets, rec_counts, colors,
+                              colors_cam_stride, backgrounds, C, G, D0, with_depth, width, height, tile_size, tile_w,
+                              tile_h, normalize_depth, render_alphas, last_ids, acc_depth, v_render_colors,
+                              v_render_alphas, hit_bits, v_means2d, v_conics, v_colors, v_opacities, v_depths, stream);
+}
+
+extern "C" int d4_blend_bwd_slab_default_variant(void) { return D4_BLEND_BWD_DEFAULT_VARIANT; }
+
+extern "C" int d4_blend_bwd_slab_variant(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
+                                         const float *colors, int64_t colors_cam_stride, const float *backgrounds,
+                                         int C, int G, int D0, int with_depth, int width, int height, int tile_size,
+                                         int tile_w, int tile_h, int normalize_depth, const float *render_alphas,
+                                         const int32_t *last_ids, const float *acc_depth, const float *v_render_colors,
+                                         const float *v_render_alphas, const uint32_t *hit_bits, float *v_means2d,
+                                         float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
+                                         int variant, d4_stream_t stream) {
+    return blend_bwd_slab_any("d4_blend_bwd_slab_variant", variant, recs, tile_offsets, rec_counts, colors,
+                              colors_cam_stride, backgrounds, C, G, D0, with_depth, width, height, tile_size, tile_w,
+                              tile_h, normalize_depth, render_alphas, last_ids, acc_depth, v_render_colors,
+                              v_render_alphas, hit_bits, v_means2d, v_conics, v_colors, v_opacities, v_depths, stream);
 }

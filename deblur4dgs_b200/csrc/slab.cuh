@@ -147,5 +147,16 @@ int launch_blend_bwd_slab(int D0, bool depth, const SlabArgs &a, const float *re
                           const float *acc_depth, const float *v_render_colors, const float *v_render_alphas,
                           float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, float *v_depths,
                           cudaStream_t st);
+// blend_slab_bwd_tc.cu: the same backward with the per-group contractions on mma.sync (3xTF32); variant 1 = the
+// gradient sums (phase 2), 2 = also <c_g, v_out> (phase 1).  Returns -1 when the call is not served by it
+// (D0 != 16, or gradient rows that are not 8-byte aligned).
+int launch_blend_bwd_slab_tc(int variant, int D0, bool depth, const SlabArgs &a, const float *render_alphas,
+                             const int32_t *last_ids, const float *acc_depth, const float *v_render_colors,
+                             const float *v_render_alphas, float *v_means2d, float *v_conics, float *v_colors,
+                             float *v_opacities, float *v_depths, cudaStream_t st);
+// what d4_blend_bwd_slab runs (d4_blend_bwd_slab_variant selects explicitly)
+#ifndef D4_BLEND_BWD_DEFAULT_VARIANT
+#define D4_BLEND_BWD_DEFAULT_VARIANT 2
+#endif
 
 }  // namespace d4

@@ -40,6 +40,8 @@ BINNING_METHOD = "auto"  # "auto" | "bucket" | "radix" (see bin_tiles)
 BLEND_PATH = "slab"
 BWD_MODE = 0  # direct path only: 0 = grouped backward kernel, 1 = warp-shuffle backward kernel
 SLAB_D0 = (4, 8, 16, 32)  # colour widths the slab kernels are built for (rasterization() pads)
+# slab backward formulation: None = the library default, 0 = fp32 pipe, 1 / 2 = tensor cores (d4_blend_bwd_slab_variant)
+SLAB_BWD_VARIANT = None
 
 
 class RenderCapacity:
@@ -547,15 +549,20 @@ class _BlendSlab(torch.autograd.Function):
         n_m, n_c, n_col, n_o, n_d = C * G * 2, C * G * 3, colors.numel(), G, (C * G if with_depth else 0)
         ws = torch.zeros((n_m + n_c + n_col + n_o + n_d,), dtype=torch.float32, device=dev)
         _cabi.count_fill()
-        v_means2d = ws[:n_m].view(C, G, 2)
-        v_conics = ws[n_m:n_m + n_c].view(C, G, 3)
-        v_colors = ws[n_m + n_c:n_m + n_c + n_col].view(colors.shape)
-        v_opacities = ws[n_m + n_c + n_col:n_m + n_c + n_col + n_o].view(oshape)
-        v_depths = ws[n_m + n_c + n_col + n_o:].view(C, G) if with_depth else None
-        call("d4_blend_bwd_slab", ptr(recs), ptr(isect_offsets), ptr(rec_counts), ptr(colors), ccs, ptr(backgrounds), C, G,
-             D0, int(with_depth), width, height, tile_size, tile_w, tile_h, normalize_depth, ptr(render_alphas),
-             ptr(last_ids), ptr(acc_depth), ptr(v_rc), ptr(v_ra), ptr(hit_bits), ptr(v_means2d), ptr(v_conics),
-             ptr(v_colors), ptr(v_opacities), ptr(v_depths), stream_ptr())
+        # colour rows first, then the xy pairs: both start 8-byte aligned (vectorised reductions in the kernel)
+        v_colors = ws[:n_col].view(colors.shape)
+        v_means2d = ws[n_col:n_col + n_m].view(C, G, 2)
+        v_conics = ws[n_col + n_m:n_col + n_m + n_c].view(C, G, 3)
+        v_opacities = ws[n_col + n_m + n_c:n_col + n_m + n_c + n_o].view(oshape)
+        v_depths = ws[n_col + n_m + n_c + n_o:].view(C, G) if with_depth else None
+        args = (ptr(recs), ptr(isect_offsets), ptr(rec_counts), ptr(colors), ccs, ptr(backgrounds), C, G,
+                D0, int(with_depth), width, height, tile_size, tile_w, tile_h, normalize_depth, ptr(render_alphas),
+                ptr(last_ids), ptr(acc_depth), ptr(v_rc), ptr(v_ra), ptr(hit_bits), ptr(v_means2d), ptr(v_conics),
+                ptr(v_colors), ptr(v_opacities), ptr(v_depths))
+        if SLAB_BWD_VARIANT is None:
+            call("d4_blend_bwd_slab", *args, stream_ptr())
+        else:
+            call("d4_blend_bwd_slab_variant", *args, int(SLAB_BWD_VARIANT), stream_ptr())
         v_backgrounds = None
         if backgrounds is not None and ctx.needs_input_grad[5]:
             v_backgrounds = (v_rc[..., :D0] * (1.0 - render_alphas)).sum(dim=(1, 2))

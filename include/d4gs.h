@@ -213,6 +213,20 @@ int d4_blend_bwd_slab(const void *recs, const int32_t *tile_offsets, const int32
                       const float *acc_depth, const float *v_render_colors, const float *v_render_alphas,
                       const uint32_t *hit_bits, float *v_means2d, float *v_conics, float *v_colors,
                       float *v_opacities, float *v_depths, d4_stream_t stream);
+/* d4_blend_bwd_slab with the formulation chosen explicitly (same results within fp32 rounding):
+ *   variant 0  every sum on the fp32 pipe (packed FFMA2);
+ *   variant 1  the per-Gaussian gradient sums over a block's 32 pixels on mma.sync.m16n8k8 (3xTF32 split, fp32-grade);
+ *   variant 2  also the <colour, cotangent> products of the recurrence.
+ * Variants 1 / 2 serve D0 == 16 with 8-byte aligned v_colors / v_means2d; any other call runs variant 0.
+ * d4_blend_bwd_slab runs the library's default variant (d4_blend_bwd_slab_default_variant()).                    */
+int d4_blend_bwd_slab_default_variant(void);
+int d4_blend_bwd_slab_variant(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
+                              const float *colors, int64_t colors_cam_stride, const float *backgrounds, int C, int G,
+                              int D0, int with_depth, int width, int height, int tile_size, int tile_w, int tile_h,
+                              int normalize_depth, const float *render_alphas, const int32_t *last_ids,
+                              const float *acc_depth, const float *v_render_colors, const float *v_render_alphas,
+                              const uint32_t *hit_bits, float *v_means2d, float *v_conics, float *v_colors,
+                              float *v_opacities, float *v_depths, int variant, d4_stream_t stream);
 
 /* ---- a1-a6: motion-basis deformation at N sub-exposure timestamps ----------------------
  * replaces, fused: GaussianParams activations normalize(quats) / softmax(coefs)

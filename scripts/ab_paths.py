@@ -44,7 +44,8 @@ def main():
     for path in args.paths:
         name, _, mode = path.partition(":")
         rendering.BLEND_PATH = name
-        rendering.BWD_MODE = int(mode or 0)
+        rendering.BWD_MODE = int(mode or 0) if name != "slab" else 0
+        rendering.SLAB_BWD_VARIANT = int(mode) if (name == "slab" and mode) else None  # slab:0 / slab:1 / slab:2
         for _ in range(3):
             o = step()
         torch.cuda.synchronize()

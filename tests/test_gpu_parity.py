@@ -37,15 +37,17 @@ from util import golden, golden_files, quat_sign_align, rel_err, scale_err
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 # blend formulations under test: (name, BLEND_PATH, BWD_MODE, HIT_MASKS); the first is the default
+# (the optional fifth field picks the slab backward: 0 fp32 pipe, 1 / 2 tensor cores; None = the library default)
 VARIANTS = [("slab", "slab", 0, True), ("direct-gp", "direct", 0, True), ("direct-gp:reach-masks", "direct", 0, False),
-            ("direct-shfl", "direct", 1, True)]
+            ("direct-shfl", "direct", 1, True), ("slab:simt", "slab", 0, True, 0), ("slab:tc-sums", "slab", 0, True, 1),
+            ("slab:tc-both", "slab", 0, True, 2)]
 
 
 class blend_variant:
     """Select a blend formulation through the module flags of deblur4dgs_b200.rendering."""
 
-    def __init__(self, path="slab", bwd_mode=0, hit_masks=True):
-        self.new = dict(BLEND_PATH=path, BWD_MODE=bwd_mode, HIT_MASKS=hit_masks)
+    def __init__(self, path="slab", bwd_mode=0, hit_masks=True, slab_bwd=None):
+        self.new = dict(BLEND_PATH=path, BWD_MODE=bwd_mode, HIT_MASKS=hit_masks, SLAB_BWD_VARIANT=slab_bwd)
 
     def __enter__(self):
         from deblur4dgs_b200 import rendering
@@ -131,10 +133,10 @@ def check_raster_against(name, inp, W, H, mode, ref, tol_grad=1e-4, variants=VAR
     """ref: dict with oracle outputs (numpy)."""
     vc, va = T(ref["v_render_colors"]), T(ref["v_render_alphas"])
     first = True
-    for tag, path, bwd_mode, hit_masks in variants:
-        with blend_variant(path, bwd_mode, hit_masks):
+    for tag, *variant in variants:
+        with blend_variant(*variant):
             t, rc, ra, meta = run_cuda_raster(inp, W, H, mode)
-            if first or bwd_mode == 0 and hit_masks:  # the forward differs between the slab and the direct path only
+            if first or len(variant) == 3 and variant[1] == 0 and variant[2]:  # the forward differs between the slab and the direct path only
                 # ---- bit-exact integer / projection outputs
                 for k in ["radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"]:
                     assert np.array_equal(meta[k].cpu().numpy(), ref[k]), f"{name}: {k} differs"
@@ -226,7 +228,7 @@ def test_rasterization_baseline_configs_vs_oracle(cfg):
     # channels, where ~100 terms of magnitude 1 cancel to ~0.02 and 1.5e-6 of absolute fp32 accumulation noise shows
     # as 1e-4 relative; the per-channel bound (1e-4 against 1e-2 of the channel scale) holds at 5.8e-5.
     check_raster_against(f"{cfg}_subexposure{i}", inp, sc.width, sc.height, "RGB+ED", ref,
-                         variants=[VARIANTS[0], VARIANTS[1]], max_edge=0.012)
+                         variants=[VARIANTS[0], VARIANTS[1], VARIANTS[5], VARIANTS[6]], max_edge=0.012)
 
 
 @pytest.mark.parametrize("G,W,H,d0,mode,C,scale_mult", [
