@@ -65,48 +65,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (the quantities of the recipe's nvidia-smi clocks
+    line), read in-process through NVML every 10 ms.  A freshly spawned ``nvidia-smi -lms`` initialises the driver
+    in a second process while the timed region runs and stalls kernel submission for tens of milliseconds -- with a
+    region of ~100 ms that was 2 ms per step; NVML is initialised once, before the warm-up."""
+    HW = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.h, self.nv, self.th = gpu_index, [], None, None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons)))
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.nv is None:
+            return
+        self.rows = []
+        self._stop.clear()
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        self._stop.set()
+        self.th.join(timeout=1)
+        sm = [r[0] for r in self.rows]
+        reasons = sorted(n for n, bit in self.HW.items() if any(r[1] & bit for r in self.rows))
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------ #
@@ -215,6 +228,8 @@ def main():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--frame", type=int, default=0)
+    ap.add_argument("--profile-pass", action="store_true",
+                    help="take the per-kernel CUDA events in a separate pass instead of inside the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -304,7 +319,9 @@ def main():
         grads = [p[k].grad for k in param_names]
         if world > 1:
             allreduce_sum_(grads)
-        return (img, acc, grads) if want_outputs else None
+        # detached: a later `pinned.copy_(img)` of a tensor that still carries its graph would be recorded by autograd and
+        # chain every step's graph (and through its leaves every step's gradients) onto the persistent host buffer
+        return (img.detach(), acc.detach(), grads) if want_outputs else None
 
     if world == 1 or args.shard == "frames":
         frames_per_step_local = N
@@ -314,16 +331,17 @@ def main():
         frames_per_step_local = len(shard_indices(N, rank, world))
     frames_per_step_global = N * world if args.shard == "frames" else N
 
+    sampler = ClockSampler(local_rank)  # NVML initialised before the warm-up, sampled during the timed region
     for _ in range(args.warmup):
         step(sc)
     torch.cuda.synchronize()
 
     # ---- timed region 1: kernel-resident throughput (inputs already in HBM) ----------------
-    prof = {}
-    _cabi.PROFILE = prof  # per-C-ABI-call CUDA events on the launching stream (see _cabi.call)
     _cabi.FILLS = 0       # torch-side zero-fill kernels issued by the op code
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    prof = {}
+    if not args.profile_pass:
+        _cabi.PROFILE = prof  # per-C-ABI-call CUDA events on the launching stream (see _cabi.call)
+    if rank == 0 and not os.environ.get("D4_BENCH_NO_SAMPLER"):
         sampler.start()
     if world > 1:
         dist.barrier()
@@ -336,16 +354,24 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 and sampler.th is not None else None
     _cabi.PROFILE = None
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    fills_per_step = _cabi.FILLS / args.steps
+    if args.profile_pass:
+        # --profile-pass: the per-call events are taken in a separate pass of the same steps instead of inside the
+        # timed region (A/B of the event overhead: 32 event records per step)
+        _cabi.PROFILE = prof
+        for _ in range(args.steps):
+            step(sc)
+        torch.cuda.synchronize()
+        _cabi.PROFILE = None
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in prof.items()}
     # every kernel of a step: the library's own (per C-ABI call) + the zero-fills of the op code (torch kernels)
     own_launches_per_step = sum(len(v) * _cabi.LAUNCHES.get(k, 1) for k, v in prof.items()) / args.steps
-    fills_per_step = _cabi.FILLS / args.steps
     launches_per_step = own_launches_per_step + fills_per_step
     if cap is not None:
         cap.check()  # raises if any timed step overflowed the binning capacity
@@ -411,13 +437,18 @@ def main():
             ev.record(up_stream)
         uploaded[k] = (dev_sets[i], ev)
 
+    trace = [] if os.environ.get("D4_E2E_TRACE") else None  # host timestamps per step (where does a stall sit?)
+
     def e2e_step(k):
+        t = [time.perf_counter()]
         if k not in uploaded:
             upload(k)
         scn, ev = uploaded.pop(k)
         torch.cuda.current_stream().wait_event(ev)
         upload(k + 1)  # overlaps this step's kernels
+        t.append(time.perf_counter())
         img, acc, grads = step(scn, want_outputs=True)
+        t.append(time.perf_counter())
         consumed[k & 1] = torch.cuda.Event()
         consumed[k & 1].record()
         outs = [img, acc] + grads
@@ -426,19 +457,26 @@ def main():
             out_host[buf] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
         if pending[buf] is not None:
             pending[buf][0].synchronize()  # the pinned buffer of step k-2 is free again
+        t.append(time.perf_counter())
+        if trace is not None:
+            t.append(torch.cuda.memory_stats().get("num_device_alloc", 0))
+            trace.append(t)
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ready)
             for h, o in zip(out_host[buf], outs):
                 h.copy_(o, non_blocking=True)
-                o.record_stream(copy_stream)
+            # no record_stream(): `outs` stay referenced (pending[buf]) until their download event has been waited for
+            # two steps later, so the allocator never hands their memory out early
             done = torch.cuda.Event()
             done.record(copy_stream)
         pending[buf] = (done, outs)
 
-    e2e_step(0)
-    e2e_step(1)
+    # warm-up of THIS loop (two live output sets change the caching allocator's steady state); the JSON line reports the
+    # cudaMalloc calls inside the timed region -- each is an implicit device sync -- and it must be 0
+    for k in range(max(4, args.warmup)):
+        e2e_step(k)
     torch.cuda.synchronize()
     uploaded.clear()  # the timed region uploads every one of its steps itself
     d2h_bytes = sum(h.numel() * h.element_size() for h in out_host[0])
@@ -446,6 +484,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    allocs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
     e0.record()
     for k in range(args.steps):
         e2e_step(k)
@@ -454,6 +493,12 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    e2e_mallocs = torch.cuda.memory_stats().get("num_device_alloc", 0) - allocs0  # cudaMalloc calls inside the region
+    if trace:
+        for k, t in enumerate(trace[-args.steps:]):
+            d = [1e3 * (b - a) for a, b in zip(t[:4], t[1:4])]
+            print(f"e2e step {k}: upload {d[0]:.2f} enqueue {d[1]:.2f} wait(k-2 download) {d[2]:.2f} ms; "
+                  f"cudaMallocs so far {t[4]}", file=sys.stderr)
     uploaded.clear()  # (the look-ahead upload of the step after the last one is not counted in h2d_bytes_per_step)
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -547,7 +592,7 @@ def main():
                          "frac_of_peak": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak},
             "kernel_ms_per_step": {k: v * len(prof[k]) / args.steps for k, v in kernel_ms.items()},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": float(ms2.item()) / args.steps},
+                    "ms_per_step": float(ms2.item()) / args.steps, "cuda_mallocs_in_timed_region": int(e2e_mallocs)},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "gpu_launches_per_step": launches_per_step,
             "gpu_launches_detail": {"libd4gs_kernels_per_step": own_launches_per_step,
