@@ -94,7 +94,7 @@ def _record_traffic(name, r, idx, units, src):
     tot = 0.0
     for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(r[idx[k]].replace(",", "")) * _UNIT.get(units[idx[k]], 1.0)
-    m = re.match(r"(?:void )?(?:d4::)?(\w+)<(?:\(int\))?(\d+)", name)
+    m = re.match(r"(?:void )?(?:d4::)?(\w+)<(?:\((?:int|bool)\))?(\d+)", name)
     key = f"{m.group(1)}<{m.group(2)}" if m else name
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
     d = json.load(open(path)) if os.path.exists(path) else {}
