@@ -44,6 +44,8 @@ PROTOTYPES = {
     "d4_tile_sort_pack": (c_int, [P, P, L, I, I, I, I, P, P, P, P, P, P, I, I, P, P, P]),
     "d4_slab_hit_words": (c_size_t, [L, L]),
     "d4_blend_fwd_slab": (c_int, [P, P, P, P, L, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P]),
+    "d4_blend_fwd_slab_default_variant": (c_int, []),
+    "d4_blend_fwd_slab_variant": (c_int, [P, P, P, P, L, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, I, P]),
     "d4_blend_bwd_slab": (c_int, [P, P, P, P, L, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P]),
     "d4_blend_bwd_slab_default_variant": (c_int, []),
     "d4_blend_bwd_slab_variant": (c_int, [P, P, P, P, L, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, I, P]),

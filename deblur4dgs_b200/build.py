@@ -28,6 +28,7 @@ UNITS = {
     "blend.cu": [],
     "blend_bwd_gp.cu": [],
     "blend_slab_fwd.cu": [],
+    "blend_slab_fwd_tc.cu": [],
     "blend_slab_bwd.cu": [],
     "blend_slab_bwd_tc.cu": [],
     "deform.cu": [],

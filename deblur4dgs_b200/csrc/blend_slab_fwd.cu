@@ -290,22 +290,52 @@ int d4::check_slab_args(const char *name, const SlabArgs &a, int D0, int tile_si
     return 0;
 }
 
+static int blend_fwd_slab_any(const char *name, int variant, const void *recs, const int32_t *tile_offsets,
+                              const int32_t *rec_counts, const float *colors, int64_t colors_cam_stride,
+                              const float *backgrounds, int C, int G, int D0, int with_depth, int width, int height,
+                              int tile_size, int tile_w, int tile_h, int normalize_depth, float *render_colors,
+                              float *render_alphas, int32_t *last_ids, float *acc_depth, uint32_t *hit_bits,
+                              d4_stream_t stream) {
+    SlabArgs a{(const float4 *)recs, tile_offsets, rec_counts, colors, colors_cam_stride, backgrounds, hit_bits,
+               C, G, width, height, tile_w, tile_h, normalize_depth};
+    if (int rc = check_slab_args(name, a, D0, tile_size)) return rc;
+    D4_CHECK_ARG(render_colors && render_alphas && last_ids, "%s: null output", name);
+    D4_CHECK_ARG(!normalize_depth || (with_depth && acc_depth), "%s: normalize_depth needs the depth channel and acc_depth", name);
+    D4_CHECK_ARG(variant >= 0 && variant <= 1, "%s: variant must be 0 (fp32 pipe) or 1 (tensor cores)", name);
+    int rc = -1;
+    if (variant == 1)  // served for the 16-colour records, otherwise falls through
+        rc = launch_blend_fwd_slab_tc(D0, with_depth != 0, hit_bits != nullptr, a, render_colors, render_alphas, last_ids,
+                                      acc_depth, as_stream(stream));
+    if (rc < 0)
+        rc = launch_blend_fwd_slab(D0, with_depth != 0, hit_bits != nullptr, a, render_colors, render_alphas, last_ids,
+                                   acc_depth, as_stream(stream));
+    if (rc != 0) {
+        set_error("%s: %s", name, rc < 0 ? "channel count not built" : "kernel configuration failed");
+        return rc < 0 ? 2 : 1;
+    }
+    D4_CHECK_LAUNCH(name);
+    return 0;
+}
+
 extern "C" int d4_blend_fwd_slab(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
                                  const float *colors, int64_t colors_cam_stride, const float *backgrounds, int C, int G,
                                  int D0, int with_depth, int width, int height, int tile_size, int tile_w, int tile_h,
                                  int normalize_depth, float *render_colors, float *render_alphas, int32_t *last_ids,
                                  float *acc_depth, uint32_t *hit_bits, d4_stream_t stream) {
-    SlabArgs a{(const float4 *)recs, tile_offsets, rec_counts, colors, colors_cam_stride, backgrounds, hit_bits,
-               C, G, width, height, tile_w, tile_h, normalize_depth};
-    if (int rc = check_slab_args("d4_blend_fwd_slab", a, D0, tile_size)) return rc;
-    D4_CHECK_ARG(render_colors && render_alphas && last_ids, "d4_blend_fwd_slab: null output");
-    D4_CHECK_ARG(!normalize_depth || (with_depth && acc_depth), "d4_blend_fwd_slab: normalize_depth needs the depth channel and acc_depth");
-    const int rc = launch_blend_fwd_slab(D0, with_depth != 0, hit_bits != nullptr, a, render_colors, render_alphas,
-                                         last_ids, acc_depth, as_stream(stream));
-    if (rc != 0) {
-        set_error("d4_blend_fwd_slab: %s", rc < 0 ? "channel count not built" : "kernel configuration failed");
-        return rc < 0 ? 2 : 1;
-    }
-    D4_CHECK_LAUNCH("d4_blend_fwd_slab");
-    return 0;
+    return blend_fwd_slab_any("d4_blend_fwd_slab", D4_BLEND_FWD_DEFAULT_VARIANT, recs, tile_offsets, rec_counts, colors,
+                              colors_cam_stride, backgrounds, C, G, D0, with_depth, width, height, tile_size, tile_w,
+                              tile_h, normalize_depth, render_colors, render_alphas, last_ids, acc_depth, hit_bits, stream);
+}
+
+extern "C" int d4_blend_fwd_slab_default_variant(void) { return D4_BLEND_FWD_DEFAULT_VARIANT; }
+
+extern "C" int d4_blend_fwd_slab_variant(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
+                                         const float *colors, int64_t colors_cam_stride, const float *backgrounds,
+                                         int C, int G, int D0, int with_depth, int width, int height, int tile_size,
+                                         int tile_w, int tile_h, int normalize_depth, float *render_colors,
+                                         float *render_alphas, int32_t *last_ids, float *acc_depth, uint32_t *hit_bits,
+                                         int variant, d4_stream_t stream) {
+    return blend_fwd_slab_any("d4_blend_fwd_slab_variant", variant, recs, tile_offsets, rec_counts, colors,
+                              colors_cam_stride, backgrounds, C, G, D0, with_depth, width, height, tile_size, tile_w,
+                              tile_h, normalize_depth, render_colors, render_alphas, last_ids, acc_depth, hit_bits, stream);
 }

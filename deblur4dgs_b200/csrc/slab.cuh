@@ -154,6 +154,14 @@ int launch_blend_bwd_slab_tc(int variant, int D0, bool depth, const SlabArgs &a,
                              const int32_t *last_ids, const float *acc_depth, const float *v_render_colors,
                              const float *v_render_alphas, float *v_means2d, float *v_conics, float *v_colors,
                              float *v_opacities, float *v_depths, cudaStream_t st);
+// blend_slab_fwd_tc.cu: the forward with the colour accumulation of 16 queued records at a time on mma.sync
+// (O += W^T . C, 3xTF32).  Returns -1 when the call is not served by it (D0 != 16).
+int launch_blend_fwd_slab_tc(int D0, bool depth, bool masks, const SlabArgs &a, float *render_colors,
+                             float *render_alphas, int32_t *last_ids, float *acc_depth, cudaStream_t st);
+// what d4_blend_fwd_slab runs (d4_blend_fwd_slab_variant selects explicitly)
+#ifndef D4_BLEND_FWD_DEFAULT_VARIANT
+#define D4_BLEND_FWD_DEFAULT_VARIANT 0
+#endif
 // what d4_blend_bwd_slab runs (d4_blend_bwd_slab_variant selects explicitly)
 #ifndef D4_BLEND_BWD_DEFAULT_VARIANT
 #define D4_BLEND_BWD_DEFAULT_VARIANT 2

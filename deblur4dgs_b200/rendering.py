@@ -42,6 +42,8 @@ BWD_MODE = 0  # direct path only: 0 = grouped backward kernel, 1 = warp-shuffle 
 SLAB_D0 = (4, 8, 16, 32)  # colour widths the slab kernels are built for (rasterization() pads)
 # slab backward formulation: None = the library default, 0 = fp32 pipe, 1 / 2 = tensor cores (d4_blend_bwd_slab_variant)
 SLAB_BWD_VARIANT = None
+# slab forward formulation: None = the library default, 0 = fp32 pipe, 1 = queued + tensor cores (d4_blend_fwd_slab_variant)
+SLAB_FWD_VARIANT = None
 
 
 class RenderCapacity:
@@ -524,9 +526,13 @@ class _BlendSlab(torch.autograd.Function):
             words = _cabi.lib().d4_slab_hit_words(recs.shape[0], n_seg)
             alloc = torch.zeros if HIT_MASK_TAP is not None else torch.empty  # every word the backward reads is written
             hit_bits = alloc((words,), dtype=torch.int32, device=dev)
-        call("d4_blend_fwd_slab", ptr(recs), ptr(isect_offsets), ptr(rec_counts), ptr(colors), ccs, ptr(backgrounds), C, G,
-             D0, int(with_depth), width, height, tile_size, tile_w, tile_h, int(normalize_depth), ptr(render_colors),
-             ptr(render_alphas), ptr(last_ids), ptr(acc_depth), ptr(hit_bits), stream_ptr())
+        fargs = (ptr(recs), ptr(isect_offsets), ptr(rec_counts), ptr(colors), ccs, ptr(backgrounds), C, G,
+                 D0, int(with_depth), width, height, tile_size, tile_w, tile_h, int(normalize_depth), ptr(render_colors),
+                 ptr(render_alphas), ptr(last_ids), ptr(acc_depth), ptr(hit_bits))
+        if SLAB_FWD_VARIANT is None:
+            call("d4_blend_fwd_slab", *fargs, stream_ptr())
+        else:
+            call("d4_blend_fwd_slab_variant", *fargs, int(SLAB_FWD_VARIANT), stream_ptr())
         if HIT_MASK_TAP is not None:
             HIT_MASK_TAP.append({"hit_bits": hit_bits, "recs": recs, "rec_counts": rec_counts,
                                  "isect_offsets": isect_offsets, "last_ids": last_ids})

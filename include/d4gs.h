@@ -206,6 +206,18 @@ int d4_blend_fwd_slab(const void *recs, const int32_t *tile_offsets, const int32
                       int D0, int with_depth, int width, int height, int tile_size, int tile_w, int tile_h,
                       int normalize_depth, float *render_colors, float *render_alphas, int32_t *last_ids,
                       float *acc_depth, uint32_t *hit_bits, d4_stream_t stream);
+/* d4_blend_fwd_slab with the formulation chosen explicitly (same decisions -- alphas, last_ids, hit words -- bit for
+ * bit; colours within fp32 rounding):
+ *   variant 0  every accumulation on the fp32 pipe (packed FFMA2), a record is composited when it is met;
+ *   variant 1  records are queued 16 at a time per 8x4 pixel block and their colours accumulated as
+ *              O[32 x 16] += W^T . C on mma.sync.m16n8k8 (3xTF32 split); serves D0 == 16, else runs variant 0.
+ * d4_blend_fwd_slab runs the library's default variant (d4_blend_fwd_slab_default_variant()).                     */
+int d4_blend_fwd_slab_default_variant(void);
+int d4_blend_fwd_slab_variant(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
+                              const float *colors, int64_t colors_cam_stride, const float *backgrounds, int C, int G,
+                              int D0, int with_depth, int width, int height, int tile_size, int tile_w, int tile_h,
+                              int normalize_depth, float *render_colors, float *render_alphas, int32_t *last_ids,
+                              float *acc_depth, uint32_t *hit_bits, int variant, d4_stream_t stream);
 int d4_blend_bwd_slab(const void *recs, const int32_t *tile_offsets, const int32_t *rec_counts,
                       const float *colors, int64_t colors_cam_stride, const float *backgrounds, int C, int G,
                       int D0, int with_depth, int width, int height, int tile_size, int tile_w, int tile_h,

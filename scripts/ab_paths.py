@@ -45,7 +45,10 @@ def main():
         name, _, mode = path.partition(":")
         rendering.BLEND_PATH = name
         rendering.BWD_MODE = int(mode or 0) if name != "slab" else 0
-        rendering.SLAB_BWD_VARIANT = int(mode) if (name == "slab" and mode) else None  # slab:0 / slab:1 / slab:2
+        # slab:<bwd>[:<fwd>] -- e.g. slab:2:1 = tensor-core backward + queued tensor-core forward
+        bm, _, fm = mode.partition(":")
+        rendering.SLAB_BWD_VARIANT = int(bm) if (name == "slab" and bm) else None
+        rendering.SLAB_FWD_VARIANT = int(fm) if (name == "slab" and fm) else None
         for _ in range(3):
             o = step()
         torch.cuda.synchronize()

@@ -40,14 +40,17 @@ DEV = "cuda"
 # (the optional fifth field picks the slab backward: 0 fp32 pipe, 1 / 2 tensor cores; None = the library default)
 VARIANTS = [("slab", "slab", 0, True), ("direct-gp", "direct", 0, True), ("direct-gp:reach-masks", "direct", 0, False),
             ("direct-shfl", "direct", 1, True), ("slab:simt", "slab", 0, True, 0), ("slab:tc-sums", "slab", 0, True, 1),
-            ("slab:tc-both", "slab", 0, True, 2)]
+            ("slab:tc-both", "slab", 0, True, 2), ("slab:fwd-tc", "slab", 0, True, 2, 1),
+            ("slab:fwd-simt", "slab", 0, True, 0, 0)]
+# (sixth field: the slab forward -- 0 fp32 pipe, 1 queued + tensor cores; None = the library default)
 
 
 class blend_variant:
     """Select a blend formulation through the module flags of deblur4dgs_b200.rendering."""
 
-    def __init__(self, path="slab", bwd_mode=0, hit_masks=True, slab_bwd=None):
-        self.new = dict(BLEND_PATH=path, BWD_MODE=bwd_mode, HIT_MASKS=hit_masks, SLAB_BWD_VARIANT=slab_bwd)
+    def __init__(self, path="slab", bwd_mode=0, hit_masks=True, slab_bwd=None, slab_fwd=None):
+        self.new = dict(BLEND_PATH=path, BWD_MODE=bwd_mode, HIT_MASKS=hit_masks, SLAB_BWD_VARIANT=slab_bwd,
+                        SLAB_FWD_VARIANT=slab_fwd)
 
     def __enter__(self):
         from deblur4dgs_b200 import rendering
@@ -132,11 +135,13 @@ def image_errors(name, tag, got_c, got_a, ref, max_edge=0.003, tol_spec=3e-4):
 def check_raster_against(name, inp, W, H, mode, ref, tol_grad=1e-4, variants=VARIANTS, max_edge=0.003, tol_spec=3e-4):
     """ref: dict with oracle outputs (numpy)."""
     vc, va = T(ref["v_render_colors"]), T(ref["v_render_alphas"])
-    first = True
+    forwards_seen = set()
     for tag, *variant in variants:
         with blend_variant(*variant):
             t, rc, ra, meta = run_cuda_raster(inp, W, H, mode)
-            if first or len(variant) == 3 and variant[1] == 0 and variant[2]:  # the forward differs between the slab and the direct path only
+            fwd_impl = (variant[0], variant[4] if len(variant) > 4 else None)  # (blend path, slab forward variant)
+            if fwd_impl not in forwards_seen:  # every distinct forward implementation gets the full forward check
+                forwards_seen.add(fwd_impl)
                 # ---- bit-exact integer / projection outputs
                 for k in ["radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"]:
                     assert np.array_equal(meta[k].cpu().numpy(), ref[k]), f"{name}: {k} differs"
@@ -145,7 +150,6 @@ def check_raster_against(name, inp, W, H, mode, ref, tol_grad=1e-4, variants=VAR
                     a, b = meta[k].detach().cpu().numpy()[vis], ref[k][vis]
                     assert np.array_equal(a.view(np.int32), b.view(np.int32)), f"{name}: {k} bits differ"
                 image_errors(name, tag, rc.detach().cpu().numpy(), ra.detach().cpu().numpy(), ref, max_edge, tol_spec)
-                first = False
             # ---- gradients
             meta["means2d"].retain_grad()
             ((rc * vc).sum() + (ra * va).sum()).backward()
@@ -228,7 +232,7 @@ def test_rasterization_baseline_configs_vs_oracle(cfg):
     # channels, where ~100 terms of magnitude 1 cancel to ~0.02 and 1.5e-6 of absolute fp32 accumulation noise shows
     # as 1e-4 relative; the per-channel bound (1e-4 against 1e-2 of the channel scale) holds at 5.8e-5.
     check_raster_against(f"{cfg}_subexposure{i}", inp, sc.width, sc.height, "RGB+ED", ref,
-                         variants=[VARIANTS[0], VARIANTS[1], VARIANTS[5], VARIANTS[6]], max_edge=0.012)
+                         variants=[VARIANTS[0], VARIANTS[1], VARIANTS[5], VARIANTS[6], VARIANTS[7], VARIANTS[8]], max_edge=0.012)
 
 
 @pytest.mark.parametrize("G,W,H,d0,mode,C,scale_mult", [
@@ -277,15 +281,19 @@ def test_hit_masks_match_oracle():
         sc = make_scene(G=G, width=W, height=H, K=4, N=1, seed=G + W, scale_mult=scale_mult)
         inp = scene_inputs(sc, d0, C)
         taps = {}
-        for path in ("slab", "direct"):
+        for path, fwd in (("slab", 0), ("slab", 1), ("direct", None)):  # both slab forwards (fp32 pipe, queued + MMA)
             rendering.HIT_MASK_TAP = []
             try:
-                with blend_variant(path):
+                with blend_variant(path, slab_fwd=fwd):
                     t, rc, ra, meta = run_cuda_raster(inp, W, H, mode)
                 assert len(rendering.HIT_MASK_TAP) == 1 and rendering.HIT_MASK_TAP[0] is not None
-                taps[path] = rendering.HIT_MASK_TAP[0]
+                taps[path if not fwd else "slab-tc"] = rendering.HIT_MASK_TAP[0]
             finally:
                 rendering.HIT_MASK_TAP = None
+        # the two slab forwards take the same decisions: hit words and last contributing records bit for bit
+        assert torch.equal(taps["slab"]["last_ids"], taps["slab-tc"]["last_ids"])
+        if d0 == 16:
+            assert torch.equal(taps["slab"]["hit_bits"], taps["slab-tc"]["hit_bits"]), "hit words of the two slab forwards differ"
         opac = np.broadcast_to(inp["opacities"][None], (C, G))
         offs, fids = meta["isect_offsets"].cpu().numpy(), meta["flatten_ids"].cpu().numpy()
         ref, edge = orc.hit_masks(meta["means2d"].detach().cpu().numpy(), meta["conics"].detach().cpu().numpy(), opac, W, H, 16,
