@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c5"])
-    ap.add_argument("--shard", default="frames", choices=["frames", "subexposures", "bands"],
+    ap.add_argument("--shard", default="frames", choices=["frames", "subexposures", "bands", "rows"],
                     help="frames: one blurry frame per rank (weak scaling, the headline); bands: ONE frame's "
                          "(sub-exposure, tile-row band) units over the ranks (strong scaling, BASELINE configs[3]; also "
                          "measured as the 'strong' object of every multi-GPU frames run); subexposures: round-robin "
@@ -238,7 +238,8 @@ def main():
     import torch.distributed as dist
     from deblur4dgs_b200 import _cabi
     from deblur4dgs_b200 import parallel
-    from deblur4dgs_b200.parallel import allreduce_sum_, render_frame_banded, render_frame_sharded, shard_indices
+    from deblur4dgs_b200.parallel import (allreduce_sum_, render_frame_banded, render_frame_rows, render_frame_sharded,
+                                          shard_indices)
     from deblur4dgs_b200.rendering import RenderCapacity
     from deblur4dgs_b200.scene import assemble_gaussians, render_subexposures
     from deblur4dgs_b200.synthetic import CONFIGS, make_config
@@ -280,6 +281,7 @@ def main():
     # a step (the first warm-up step synchronises once to learn the sizes; overflow is checked after the timed regions)
     cap = None if args.sync else RenderCapacity()
     cap_bands = None if args.sync else RenderCapacity()
+    cap_rows = None if args.sync else RenderCapacity()
 
     def step(scn, want_outputs=False, shard=None):
         """One blurry frame forward + backward from the raw scene parameters."""
@@ -291,11 +293,11 @@ def main():
                                                   extra=scn.extra_channels if scn.extra_channels.shape[1] else None,
                                                   with_mask=True)
 
-        def local(times, RTs, combine, row_windows=None, camera_of=None):
+        def local(times, RTs, combine, row_windows=None, camera_of=None, capacity=None):
             return render_subexposures(p["fg_means"], p["fg_quats"], p["motion_coefs"], p["bg_means"], p["bg_quats"],
                                        p["rots"], p["transls"], times, RTs, scales, opac, colors, scn.w2c, scn.K, W, H,
                                        backgrounds=bg, render_mode="RGB+ED", combine=combine, ref_quirk=True,
-                                       capacity=cap if row_windows is None else cap_bands, row_windows=row_windows,
+                                       capacity=capacity or (cap if row_windows is None else cap_bands), row_windows=row_windows,
                                        camera_of=camera_of)
 
         if world > 1 and shard == "bands":
@@ -303,6 +305,11 @@ def main():
                 o = local(t, r, False, (row0, band_h), camera_of)
                 return o["exposure_imgs"], o["exposure_alphas"]
             img, acc = render_frame_banded(scn.times, scn.RTs, H, render_units, ref_quirk=True)
+        elif world > 1 and shard == "rows":
+            def render_units(t, r, camera_of, row0, band_h):
+                o = local(t, r, False, (row0, band_h), camera_of, capacity=cap_rows)
+                return o["exposure_imgs"], o["exposure_alphas"]
+            img, acc = render_frame_rows(scn.times, scn.RTs, H, render_units, ref_quirk=True)
         elif world > 1 and shard == "subexposures":
             def render_local(t, r):
                 o = local(t, r, False)
@@ -325,7 +332,7 @@ def main():
 
     if world == 1 or args.shard == "frames":
         frames_per_step_local = N
-    elif args.shard == "bands":
+    elif args.shard in ("bands", "rows"):
         frames_per_step_local = N / world  # N (sub-exposure, band) units = N / world whole sub-exposure frames
     else:
         frames_per_step_local = len(shard_indices(N, rank, world))
@@ -511,37 +518,46 @@ def main():
     if world > 1 and args.shard == "frames":
         # the SAME frame on every rank
         sc_frame = make_config(args.config, seed=seed, scale_mult=args.scale_mult).to(dev) if not args.checkpoint else sc
-        for _ in range(max(3, args.warmup)):
-            step(sc_frame, shard="bands")
-        torch.cuda.synchronize()
-        cprof, kprof = {}, {}
-        parallel.PROFILE = cprof
-        _cabi.PROFILE = kprof
-        dist.barrier()
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(args.steps):
-            step(sc_frame, shard="bands")
-        s1.record()
-        dist.barrier()
-        torch.cuda.synchronize()
-        parallel.PROFILE = None
-        _cabi.PROFILE = None
-        if cap_bands is not None:
-            cap_bands.check()
-        coll = sum(a.elapsed_time(b) for v in cprof.values() for a, b in v) / args.steps
-        t = torch.tensor([s0.elapsed_time(s1), coll], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        strong_ms = float(t[0].item()) / args.steps
-        strong = {"partition": f"{N} sub-exposures x {world} tile-row bands, {N} units per rank", "frames_per_s": N / (strong_ms * 1e-3),
-                  "ms_per_blurry_frame": strong_ms, "speedup_vs_1gpu": (ms_total / args.steps) / strong_ms,
-                  "collective_ms": float(t[1].item()),
-                  "collectives": {k: len(v) / args.steps for k, v in cprof.items()},
-                  "collective_ms_by_tag": {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in cprof.items()},
-                  "kernel_ms_per_step": {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in kprof.items()},
-                  "note": "speedup against this run's own one-frame-per-GPU step (ms_per_step, which includes the gradient "
-                          "all-reduce); collective_ms = CUDA-event time inside the NCCL calls (max over ranks)"}
+
+        def strong_leg(mode, partition):
+            for _ in range(max(3, args.warmup)):
+                step(sc_frame, shard=mode)
+            torch.cuda.synchronize()
+            cprof, kprof = {}, {}
+            parallel.PROFILE = cprof
+            _cabi.PROFILE = kprof
+            dist.barrier()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                step(sc_frame, shard=mode)
+            s1.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            parallel.PROFILE = None
+            _cabi.PROFILE = None
+            for cp_ in (cap_bands, cap_rows):
+                if cp_ is not None and cp_.ready:
+                    cp_.check()
+            coll = sum(a.elapsed_time(b) for v in cprof.values() for a, b in v) / args.steps
+            t = torch.tensor([s0.elapsed_time(s1), coll], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            strong_ms = float(t[0].item()) / args.steps
+            return {"partition": partition, "frames_per_s": N / (strong_ms * 1e-3),
+                    "ms_per_blurry_frame": strong_ms, "speedup_vs_1gpu": (ms_total / args.steps) / strong_ms,
+                    "collective_ms": float(t[1].item()),
+                    "collectives": {k: len(v) / args.steps for k, v in cprof.items()},
+                    "collective_ms_by_tag": {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in cprof.items()},
+                    "kernel_ms_per_step": {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in kprof.items()},
+                    "note": "speedup against this run's own one-frame-per-GPU step (ms_per_step, which includes the "
+                            "gradient all-reduce); collective_ms = CUDA-event time inside the NCCL calls (max over ranks)"}
+
+        # band-major: rank r renders row band r of all N sub-exposures, local combine, one all-gather
+        strong = strong_leg("rows", f"{world} tile-row bands, every rank renders its band of all {N} sub-exposures; "
+                                    "local N-way combine, one all-gather of the combined band")
+        # the 2-D partition of round 2 (sub-exposure-major units, 4 all-reduces) for comparison
+        strong["alt_2d_units"] = strong_leg("bands", f"{N} sub-exposures x {world} tile-row bands, {N} units per rank")
 
     if rank == 0:
         value = frames_per_step_global * args.steps / (ms_total * 1e-3)

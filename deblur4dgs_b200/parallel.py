@@ -24,6 +24,13 @@ The path shards two ways, both with replicated parameters (~20 MB at config c3):
   torch.max / min do); backward exchange: the SUM all-reduce of the parameter gradients.  Reproduces the
   reference's in-place alias quirk (``ref_quirk``), i.e. it is training-equivalent to the single-GPU path.
 
+* ``"rows"`` (strong scaling, band-major; what bench.py's strong leg runs): rank r renders the tile-row band r of ALL N
+  sub-exposures (one "C = N cameras" launch with a common row window).  Every pixel's N samples then live on ONE
+  rank, so the N-way combine (scene_model.py:386-397, alias quirk included) is the single-GPU kernel on the band --
+  no image reduction across ranks at all.  Forward exchange: ONE all-gather of the combined band (image | alpha),
+  only because the callers expect the whole image on every rank; backward: a slice of the (replicated) image
+  cotangent, then the SUM all-reduce of the parameter gradients that every mode has.
+
 Everything here is host logic over ``torch.distributed``; the kernels are unchanged.
 """
 from __future__ import annotations
@@ -316,3 +323,69 @@ def render_frame_banded(times: Tensor, RTs: Optional[Tensor], height: int, rende
     row0 = torch.as_tensor([b * band_h for b in bands], dtype=torch.int32, device=times.device)
     imgs, alphas = render_units(times[idx], None if RTs is None else RTs[idx], camera_of, row0, band_h)
     return combine_band_units(imgs, alphas, subs, bands, N, n_bands, height, ref_quirk, group)
+
+
+# ------------------------------------------------------------------------------------------------ #
+# band-major partition: rank r owns row band r of every sub-exposure; the combine is local
+# ------------------------------------------------------------------------------------------------ #
+class _GatherBands(torch.autograd.Function):
+    """band [1, band_h, W, D] of this rank -> the whole image [1, H, W, D] on every rank (all-gather along the rows).
+    Backward: the rows of this rank out of the image cotangent, which every rank holds in full (each computes the
+    loss on the whole replicated image), so no reduction is needed."""
+
+    @staticmethod
+    def forward(ctx, band, height, group):
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        _, bh, W, D = band.shape
+        band = band.contiguous()
+        if world > 1:
+            full = torch.empty((world, bh, W, D), dtype=band.dtype, device=band.device)
+            prof = PROFILE
+            if prof is not None and band.is_cuda:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dist.all_gather_into_tensor(full, band, group=group)
+                e1.record()
+                prof.setdefault("band_gather", []).append((e0, e1))
+            else:
+                dist.all_gather_into_tensor(full, band, group=group)
+        else:
+            full = band
+        ctx.cfg = (rank, bh, height)
+        return full.reshape(1, world * bh, W, D)[:, :height]
+
+    @staticmethod
+    def backward(ctx, v_full):
+        rank, bh, height = ctx.cfg
+        lo, hi = rank * bh, min((rank + 1) * bh, height)
+        v_band = v_full.new_zeros((1, bh) + tuple(v_full.shape[2:]))
+        if hi > lo:
+            v_band[:, :hi - lo] = v_full[:, lo:hi]
+        return v_band, None, None
+
+
+def render_frame_rows(times: Tensor, RTs: Optional[Tensor], height: int, render_units, ref_quirk: bool = True, group=None,
+                      combine=None):
+    """Strong scaling, band-major partition: this rank renders rows ``[rank * band_h, (rank + 1) * band_h)`` of all N
+    sub-exposures of ONE frame, combines them locally and all-gathers the combined band.
+
+    ``render_units`` as in ``render_frame_banded``.  Returns the combined image [1,H,W,D] and alpha [1,H,W,1],
+    replicated on every rank -- the same values as the single-GPU path (the combine sees exactly the N samples of a
+    pixel in sub-exposure order, ``ref_quirk`` included).  ``combine(imgs, alphas) -> (img, alpha)`` replaces the
+    CUDA combine kernel (the CPU tests of this host logic pass the reference expression)."""
+    from .scene import combine_subexposures
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    N = times.shape[0]
+    band_h, _ = band_layout(height, world)
+    camera_of = torch.arange(N, dtype=torch.long, device=times.device)
+    row0 = torch.full((N,), rank * band_h, dtype=torch.int32, device=times.device)
+    imgs, alphas = render_units(times, RTs, camera_of, row0, band_h)  # [N,1,band_h,W,D], [N,1,band_h,W,1]
+    D = imgs.shape[-1]
+    if combine is not None:
+        img_b, acc_b = combine(imgs, alphas)
+    else:
+        img_b, acc_b = combine_subexposures(imgs, alphas, 3 if D > 3 else -1, 16 if D > 16 else -1, ref_quirk=ref_quirk)
+    both = _GatherBands.apply(torch.cat([img_b, acc_b], dim=-1), int(height), group)  # one collective for image | alpha
+    return both[..., :D], both[..., D:]

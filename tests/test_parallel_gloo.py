@@ -48,6 +48,7 @@ def _worker(rank, world, port, q):
         ok = ok and torch.equal(ts[0], torch.full((3, 4), float(tot))) and torch.equal(ts[2], torch.arange(5.0) * tot)
         ok = ok and torch.equal(ts[3], torch.ones(1000) * sum(range(world)))
         ok = ok and _band_check(rank, world)
+        ok = ok and _rows_check(rank, world)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -63,6 +64,41 @@ def _reference_combine(imgs, alphas):
     render_colors[:, :, :, 3:4] = torch.stack(allc, 0).max(0)[0][:, :, :, 3:4]
     render_colors[:, :, :, 16:17] = torch.stack(allc, 0).min(0)[0][:, :, :, 16:17]
     return render_colors, torch.stack([alphas[i] for i in range(N)], 0).mean(0)
+
+
+def _rows_check(rank, world):
+    """Band-major partition: rank r holds row band r of ALL sub-exposures, combines locally and all-gathers -- against
+    the literal reference combine of the whole image: values, and the gradient every rank's band receives."""
+    from deblur4dgs_b200.parallel import band_layout, render_frame_rows
+    N, H, W, D = 5, 40, 7, 17
+    band_h, n_bands = band_layout(H, world)
+    Hp = band_h * n_bands
+    g = torch.Generator().manual_seed(2)
+    full = torch.randn(N, 1, Hp, W, D, generator=g)
+    full[..., 3] = (torch.rand(N, 1, Hp, W, generator=g) > 0.6).float()
+    falpha = torch.rand(N, 1, Hp, W, 1, generator=g)
+    vi, va = torch.randn(1, H, W, D, generator=g), torch.randn(1, H, W, 1, generator=g)
+    leaves = {}
+
+    def render_units(times, RTs, camera_of, row0, bh):
+        assert bh == band_h and camera_of.tolist() == list(range(N)) and row0.tolist() == [rank * band_h] * N
+        leaves["i"] = full[:, :, rank * band_h:(rank + 1) * band_h].clone().requires_grad_(True)
+        leaves["a"] = falpha[:, :, rank * band_h:(rank + 1) * band_h].clone().requires_grad_(True)
+        return leaves["i"], leaves["a"]
+
+    out, oa = render_frame_rows(torch.zeros(N), None, H, render_units, combine=_reference_combine)
+    ri = full[:, :, :H].clone().requires_grad_(True)
+    ra = falpha[:, :, :H].clone().requires_grad_(True)
+    ref, refa = _reference_combine(ri, ra)
+    ok = out.shape == ref.shape and torch.allclose(out, ref, atol=1e-6) and torch.allclose(oa, refa, atol=1e-6)
+    ((out * vi).sum() + (oa * va).sum()).backward()
+    ((ref * vi).sum() + (refa * va).sum()).backward()
+    r0, r1 = rank * band_h, min((rank + 1) * band_h, H)
+    want = torch.zeros(N, 1, band_h, W, D)
+    want[:, :, :r1 - r0] = ri.grad[:, :, r0:r1]
+    wa = torch.zeros(N, 1, band_h, W, 1)
+    wa[:, :, :r1 - r0] = ra.grad[:, :, r0:r1]
+    return bool(ok and torch.allclose(leaves["i"].grad, want, atol=1e-6) and torch.allclose(leaves["a"].grad, wa, atol=1e-6))
 
 
 def _band_check(rank, world):
