@@ -251,6 +251,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1 and not os.environ.get("D4_BENCH_NO_AFFINITY"):
+        # one process per GPU: run on the CPU cores next to this GPU, so that the pinned staging buffers of the end-to-end
+        # loop are first-touched on the GPU's own NUMA node (torchrun leaves the ranks unpinned)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+        except Exception:
+            pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
