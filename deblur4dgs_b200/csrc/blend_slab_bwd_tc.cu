@@ -66,7 +66,10 @@ struct TcCfg {
         return sizeof(float) * kBlendThreads * kD0 + (DEPTH ? sizeof(float) * kBlendThreads : 0) + NW * warp_bytes() + 128;
     }
     static constexpr size_t stage_bytes() { return (size_t)kSlabChunk * (32 + 4 * kD0); }
-    static constexpr int kCtas = 3;
+#ifndef D4_TC_BWD_CTAS
+#define D4_TC_BWD_CTAS 3
+#endif
+    static constexpr int kCtas = D4_TC_BWD_CTAS;
     static constexpr int stages() {
         const size_t budget = (228 * 1024) / kCtas - 1024 - 64;
         int s = (int)((budget - fixed_bytes()) / stage_bytes());

@@ -136,11 +136,13 @@ blend_fwd_slab_kernel(SlabArgs a, float *__restrict__ render_colors, float *__re
                 uint32_t bits = __ballot_sync(0xffffffffu, (idm >> (24 + w)) & 1u);
                 uint32_t hitbits = 0u;
                 const int32_t idx0 = seg_start + k * CH;
-                // one record of the hit list for this pixel; returns true when the whole warp is finished
-                auto composite = [&](int t, float power, float L, float depth) -> bool {
+                // one record of the hit list for this pixel.  Whether the whole warp has finished is asked once per chunk,
+                // not per record (a vote + branch per composite was 12 % of the kernel's instructions): a finished warp
+                // walks the rest of its chunk with valid == false everywhere, i.e. an exponent and a vote per record
+                auto composite = [&](int t, float power, float L, float depth) {
                     const float alpha = fminf(kAlphaMax, ex2_approx(power));
                     const bool valid = !done && power <= L && alpha >= kAlphaMin;
-                    if (!__any_sync(0xffffffffu, valid)) return false;
+                    if (!__any_sync(0xffffffffu, valid)) return;
                     if constexpr (kMasks) hitbits |= 1u << t;
                     if (valid) {
                         const float next_T = T * (1.0f - alpha);
@@ -161,7 +163,6 @@ blend_fwd_slab_kernel(SlabArgs a, float *__restrict__ render_colors, float *__re
                             T = next_T;
                         }
                     }
-                    return __all_sync(0xffffffffu, done);
                 };
                 while (bits) {
                     // two hits per trip: both exponents are evaluated before either is composited
@@ -175,9 +176,10 @@ blend_fwd_slab_kernel(SlabArgs a, float *__restrict__ render_colors, float *__re
                     const float dxa = ga.x - px, dya = ga.y - py, dxb = gb.x - px, dyb = gb.y - py;
                     const float pa = fmaf(ca.z * dya, dya, fmaf(fmaf(ca.y, dya, ca.x * dxa), dxa, ga.z));
                     const float pb = fmaf(cb.z * dyb, dyb, fmaf(fmaf(cb.y, dyb, cb.x * dxb), dxb, gb.z));
-                    if (composite(ta, pa, ga.z, ca.w)) { warp_done = true; break; }
-                    if (has_b && composite(tb, pb, gb.z, cb.w)) { warp_done = true; break; }
+                    composite(ta, pa, ga.z, ca.w);
+                    if (has_b) composite(tb, pb, gb.z, cb.w);
                 }
+                warp_done = __all_sync(0xffffffffu, done);
                 if constexpr (kMasks) {
                     if (lane == 0) a.hit_bits[hb_base + (int64_t)k * kSlabConsumers] = hitbits;
                 }
