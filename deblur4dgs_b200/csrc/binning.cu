@@ -450,18 +450,24 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
     }
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[i] = i < n ? src_keys[i] : ~0ull;
+    // Key k sits at slot kp(k): within every second 16-key row (128 bytes = all 32 banks) the columns are mirrored.
+    // A stage with partner distance jj < 16 touches the same 8 of 16 columns in each of the 4 rows of a 64-key chunk
+    // -- 4 wavefronts for 32 x 8 bytes where 2 are needed; mirrored odd rows use the complementary columns (ncu before:
+    // 38 % of the kernel's shared-memory wavefronts were bank conflicts at 93 % LSU data-pipe utilisation).
+    auto kp = [](int k) { return k ^ ((k & 16) - ((k & 16) >> 4)); };
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[kp(i)] = i < n ? src_keys[i] : ~0ull;
     __syncthreads();
     // Bitonic network.  Stages with partner distance j <= 32 only exchange within aligned 64-key chunks: chunk q is
     // owned by warp q % 8 for the whole sort, so those stages need a warp barrier only.  Block barriers remain
     // around the stages with j >= 64 (6 of the 45 stages at 512 keys).
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    auto cmpx = [&](int lo, int hi, int k) {
-        const uint64_t a = s_keys[lo], b = s_keys[hi];
+    auto cmpx = [&](int lo, int hi, int k) {  // logical positions lo < hi
+        const int plo = kp(lo), phi = kp(hi);
+        const uint64_t a = s_keys[plo], b = s_keys[phi];
         const bool asc = (lo & k) == 0;
         if ((a > b) == asc) {
-            s_keys[lo] = b;
-            s_keys[hi] = a;
+            s_keys[plo] = b;
+            s_keys[phi] = a;
         }
     };
     for (int k = 2; k <= n_pad; k <<= 1) {
@@ -489,12 +495,12 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
     const int64_t cam = seg / n_tiles, tile = seg - cam * n_tiles;
     const int64_t hi_bits = (cam << (32 + tile_n_bits)) | (tile << 32);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint64_t key = s_keys[i];
+        const uint64_t key = s_keys[kp(i)];
         flatten_ids[start + i] = (int32_t)(uint32_t)key;
         isect_ids[start + i] = hi_bits | (int64_t)(key >> 32);
     }
     // packed records of the tile for the slab blend kernels, straight from the sorted keys in shared memory
-    if (pack.recs) pack_segment(pack, [&](int i) { return (int32_t)(uint32_t)s_keys[i]; }, n, start, seg, n_tiles, s_warp);
+    if (pack.recs) pack_segment(pack, [&](int i) { return (int32_t)(uint32_t)s_keys[kp(i)]; }, n, start, seg, n_tiles, s_warp);
 }
 
 }  // namespace d4
