@@ -421,7 +421,7 @@ isect_pack_kernel(PackArgs p, const int32_t *__restrict__ tile_offsets, const in
     pack_segment(p, [&](int i) { return __ldg(flatten_ids + start + i); }, end - start, start, seg, n_tiles, s_warp);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)  // 32 registers: eight CTAs per SM for the short lists of the benchmark scene
 tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__restrict__ tile_offsets, int64_t n_isects,
                  const int64_t *__restrict__ n_isects_dev, int64_t capacity, int sort_capacity,
                  int64_t *__restrict__ overflow, int64_t n_segments, int n_tiles, int tile_n_bits,
@@ -448,19 +448,107 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
         if (pack.recs && threadIdx.x == 0) pack.rec_counts[seg] = 0;
         return;
     }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int64_t cam = seg / n_tiles, tile = seg - cam * n_tiles;
+    const int64_t hi_bits = (cam << (32 + tile_n_bits)) | (tile << 32);
+    auto write_out = [&](auto key_at) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t key = key_at(i);
+            flatten_ids[start + i] = (int32_t)(uint32_t)key;
+            isect_ids[start + i] = hi_bits | (int64_t)(key >> 32);
+        }
+        // packed records of the tile for the slab blend kernels, straight from the sorted keys in shared memory
+        if (pack.recs) pack_segment(pack, [&](int i) { return (int32_t)(uint32_t)key_at(i); }, n, start, seg, n_tiles, s_warp);
+    };
+    auto kp = [](int k) { return k ^ ((k & 16) - ((k & 16) >> 4)); };  // slot of key k (see below)
+
+    // ---- long lists (stress configurations: thousands of entries per tile): 64-key runs sorted by one warp each, then
+    // log2(n / 64) merge-path levels between two halves of the buffer.  The bitonic network costs n log^2 n / 4
+    // compare-exchanges (78 stages at 4096 keys), the merges n log n element moves: measured at c5 x2 (170 M
+    // intersections, 3640 per tile on average) the network was 13.2 of the step's 26.1 ms.
+    const int n64 = (n + 63) & ~63;
+    // every thread produces E consecutive outputs per merge level; E is a power of two, so a range never straddles a pair
+    int eshift = 3;
+    while ((blockDim.x << eshift) < n64) ++eshift;
+    const int E = 1 << eshift;
+    // merged runs are stored with one slot of padding per E keys: thread t writes from slot t (E + 1), an odd stride, so
+    // the 32 lanes of a warp hit 16 distinct bank pairs (unpadded they would all hit the same one)
+    auto pm = [&](int i) { return i + (i >> eshift); };
+    const int nbuf = pm(n64) + 1;
+    if (n > 1024 && 2 * nbuf <= sort_capacity) {
+        uint64_t *buf0 = s_keys, *buf1 = s_keys + nbuf;
+        for (int i = threadIdx.x; i < n64; i += blockDim.x) buf0[kp(i)] = i < n ? src_keys[i] : ~0ull;
+        __syncthreads();
+        for (int base = w * 64; base < n64; base += n_warps * 64) {  // ascending 64-key runs, warp-local
+            for (int k = 2; k <= 64; k <<= 1)
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    const int lo = base + (((lane & ~(jj - 1)) << 1) | (lane & (jj - 1)));
+                    const int plo = kp(lo), phi = kp(lo | jj);
+                    const uint64_t a = buf0[plo], b = buf0[phi];
+                    const bool asc = k == 64 || (lo & k) == 0;
+                    if ((a > b) == asc) {
+                        buf0[plo] = b;
+                        buf0[phi] = a;
+                    }
+                    __syncwarp();
+                }
+        }
+        __syncthreads();
+        const uint64_t *src = buf0;
+        uint64_t *dst = buf1;
+        bool swz = true;  // the runs of the first level sit in the mirrored layout of the warp-local sort
+        for (int run = 64; run < n64; run <<= 1) {
+            const int o0 = threadIdx.x * E;
+            if (o0 < n64) {
+                const int pbase = o0 & ~(2 * run - 1);
+                const int a_len = min(run, n64 - pbase), b_len = min(run, n64 - pbase - a_len);
+                const int a0 = pbase, b0 = pbase + a_len, d = o0 - pbase;
+                auto at = [&](int i) { return src[swz ? kp(i) : pm(i)]; };
+                // merge path: how many of the first d outputs come from run A (keys are unique)
+                int lo = max(0, d - b_len), hi = min(d, a_len);
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (at(a0 + mid) <= at(b0 + d - 1 - mid)) lo = mid + 1;
+                    else hi = mid;
+                }
+                int i = lo, j = d - lo;
+                uint64_t a = i < a_len ? at(a0 + i) : ~0ull, b = j < b_len ? at(b0 + j) : ~0ull;
+                const int cnt = min(E, a_len + b_len - d);
+                for (int t = 0; t < cnt; ++t) {
+                    const bool take_a = a <= b;
+                    dst[pm(o0 + t)] = take_a ? a : b;
+                    if (take_a) {
+                        ++i;
+                        a = i < a_len ? at(a0 + i) : ~0ull;
+                    } else {
+                        ++j;
+                        b = j < b_len ? at(b0 + j) : ~0ull;
+                    }
+                }
+            }
+            __syncthreads();
+            const uint64_t *t2 = src;
+            src = dst;
+            dst = const_cast<uint64_t *>(t2);
+            swz = false;
+        }
+        const uint64_t *sorted = src;
+        const bool sorted_swz = swz;  // n64 == 64 cannot happen here (n > 1024), kept for clarity
+        write_out([&](int i) { return sorted[sorted_swz ? kp(i) : pm(i)]; });
+        return;
+    }
+
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
     // Key k sits at slot kp(k): within every second 16-key row (128 bytes = all 32 banks) the columns are mirrored.
     // A stage with partner distance jj < 16 touches the same 8 of 16 columns in each of the 4 rows of a 64-key chunk
     // -- 4 wavefronts for 32 x 8 bytes where 2 are needed; mirrored odd rows use the complementary columns (ncu before:
     // 38 % of the kernel's shared-memory wavefronts were bank conflicts at 93 % LSU data-pipe utilisation).
-    auto kp = [](int k) { return k ^ ((k & 16) - ((k & 16) >> 4)); };
     for (int i = threadIdx.x; i < n_pad; i += blockDim.x) s_keys[kp(i)] = i < n ? src_keys[i] : ~0ull;
     __syncthreads();
     // Bitonic network.  Stages with partner distance j <= 32 only exchange within aligned 64-key chunks: chunk q is
     // owned by warp q % 8 for the whole sort, so those stages need a warp barrier only.  Block barriers remain
     // around the stages with j >= 64 (6 of the 45 stages at 512 keys).
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     auto cmpx = [&](int lo, int hi, int k) {  // logical positions lo < hi
         const int plo = kp(lo), phi = kp(hi);
         const uint64_t a = s_keys[plo], b = s_keys[phi];
@@ -492,15 +580,7 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
         }
     }
     __syncthreads();
-    const int64_t cam = seg / n_tiles, tile = seg - cam * n_tiles;
-    const int64_t hi_bits = (cam << (32 + tile_n_bits)) | (tile << 32);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint64_t key = s_keys[kp(i)];
-        flatten_ids[start + i] = (int32_t)(uint32_t)key;
-        isect_ids[start + i] = hi_bits | (int64_t)(key >> 32);
-    }
-    // packed records of the tile for the slab blend kernels, straight from the sorted keys in shared memory
-    if (pack.recs) pack_segment(pack, [&](int i) { return (int32_t)(uint32_t)s_keys[kp(i)]; }, n, start, seg, n_tiles, s_warp);
+    write_out([&](int i) { return s_keys[kp(i)]; });
 }
 
 }  // namespace d4
@@ -569,6 +649,10 @@ static int launch_tile_sort(const char *name, const uint64_t *bucket_keys, const
                             cudaStream_t st, int bucket_stride = 0) {
     int n_pad = 1;
     while (n_pad < sort_capacity) n_pad <<= 1;
+    // long lists are merge-sorted between two halves of the buffer (tile_sort_kernel): twice the keys while three CTAs
+    // still share an SM (64 KB each) -- the packing tail of the kernel is latency-bound and needs the occupancy (measured
+    // at c5 x2: doubling 64 KB to 128 KB made the kernel slower, 13.2 -> 16.0 ms, although every tile took the merge path)
+    if (n_pad > 2048 && n_pad <= 4096) n_pad *= 2;
     const size_t smem = sizeof(uint64_t) * (size_t)n_pad;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

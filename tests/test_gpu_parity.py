@@ -630,18 +630,19 @@ def test_bucket_binning_equals_radix_binning():
         b = bin_tiles(means2d, radii, depths, 16, tw, th, tpg, method="auto")
         for x, y, name in zip(a, b, ["isect_ids", "flatten_ids", "isect_offsets"]):
             assert torch.equal(x, y), (G, name)
-    # one tile with 12 000 entries: beyond the shared-memory radix sort (8192), inside the bitonic network's capacity
-    G = 12000
-    means = torch.zeros(G, 3); means[:, 2] = torch.linspace(2, 3, G)[torch.randperm(G, generator=torch.Generator().manual_seed(1))]
-    means[::7, 2] = 2.5  # with ties
-    args = (T(means.numpy()), T(np.tile([1.0, 0, 0, 0], (G, 1)).astype(np.float32)), T(np.full((G, 3), 0.01, np.float32)),
-            T(np.eye(4, dtype=np.float32)[None]), T(np.array([[[20.0, 0, 8], [0, 20, 8], [0, 0, 1]]], np.float32)), 16, 16)
-    radii, means2d, depths, conics, tpg = fully_fused_projection(*args)
-    a = bin_tiles(means2d, radii, depths, 16, 1, 1, tpg, method="radix")
-    b = bin_tiles(means2d, radii, depths, 16, 1, 1, tpg, method="bucket")
-    assert a[0].numel() == G
-    for x, y, name in zip(a, b, ["isect_ids", "flatten_ids", "isect_offsets"]):
-        assert torch.equal(x, y), ("one big tile", name)
+    # one tile with thousands of entries: 1 500 (bitonic network, padded to 2048), 3 000 / 7 000 / 8 129 (64-key runs +
+    # merge-path levels between two halves of the buffer; odd run counts), 12 000 (too long for two halves: network)
+    for G in (1500, 3000, 7000, 8129, 12000):
+        means = torch.zeros(G, 3); means[:, 2] = torch.linspace(2, 3, G)[torch.randperm(G, generator=torch.Generator().manual_seed(1))]
+        means[::7, 2] = 2.5  # with ties
+        args = (T(means.numpy()), T(np.tile([1.0, 0, 0, 0], (G, 1)).astype(np.float32)), T(np.full((G, 3), 0.01, np.float32)),
+                T(np.eye(4, dtype=np.float32)[None]), T(np.array([[[20.0, 0, 8], [0, 20, 8], [0, 0, 1]]], np.float32)), 16, 16)
+        radii, means2d, depths, conics, tpg = fully_fused_projection(*args)
+        a = bin_tiles(means2d, radii, depths, 16, 1, 1, tpg, method="radix")
+        b = bin_tiles(means2d, radii, depths, 16, 1, 1, tpg, method="bucket")
+        assert a[0].numel() == G
+        for x, y, name in zip(a, b, ["isect_ids", "flatten_ids", "isect_offsets"]):
+            assert torch.equal(x, y), ("one big tile", G, name)
     # overflow: > capacity intersections in one tile -> "bucket" refuses, "auto" falls back to radix
     cap = _cabi.lib().d4_tile_sort_capacity()
     G = cap + 500
