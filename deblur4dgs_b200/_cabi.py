@@ -63,6 +63,7 @@ PROTOTYPES = {
     "d4_band_finalize": (c_int, [P, P, P, I, I, I, I, I, I, I, P, P, P]),
     "d4_band_bwd": (c_int, [P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P, P]),
     "d4_correlation_fwd": (c_int, [P, P, I, I, I, I, P, P]),
+    "d4_correlation_bwd": (c_int, [P, P, P, I, I, I, I, P, P, P]),
     "d4_combine_fwd": (c_int, [P, P, I, L, I, I, I, I, P, P, P, P, P]),
     "d4_combine_bwd": (c_int, [P, P, I, L, I, I, I, P, P, P, P, P]),
 }

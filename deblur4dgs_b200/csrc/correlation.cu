@@ -9,7 +9,9 @@
 // image's (32 + 8) x (8 + 8) halo tile in shared memory eight channels at a time (zero outside the image, as the
 // reference's padding), and every thread keeps the 81 sums of its pixel in registers.  No padded copies, no
 // reductions, no barriers besides the two per channel chunk; out[b, (dy+4)*9 + (dx+4), y, x] = <f1[:, y, x],
-// f2[:, y+dy, x+dx]> / C.  Forward only: the reference runs PWC-Net under torch.no_grad (loss_utils.py:171-172).
+// f2[:, y+dy, x+dx]> / C.  The backward (correlation_bwd_kernel below) restates kernel_Correlation_updateGradFirst /
+// updateGradSecond (:105-233); the reference itself never runs it (PWC-Net sits under torch.no_grad,
+// loss_utils.py:171-172), it completes the module for callers that do differentiate through the cost volume.
 #include "common.cuh"
 
 namespace d4 {
@@ -69,6 +71,49 @@ correlation_fwd_kernel(const float *__restrict__ first, const float *__restrict_
     }
 }
 
+// Backward of the cost volume: kernel_Correlation_updateGradFirst (correlation.py:105-167) and
+// kernel_Correlation_updateGradSecond (:169-233), which the reference launches once per SAMPLE (:341-381), in one
+// launch for the whole batch.  One thread per (b, c, y, x), x fastest -- the reference's mapping -- and its summation
+// order (dy outer, dx inner, fused multiply-adds, one division by C at the end):
+//   gradFirst [b,c,y,x] = (1/C) sum_{dy,dx} gradOutput[b, op, y, x]         * second[b, c, y+dy, x+dx]
+//   gradSecond[b,c,y,x] = (1/C) sum_{dy,dx} gradOutput[b, op, y-dy, x-dx]   * first [b, c, y-dy, x-dx]
+// with op = (dy+4)*9 + (dx+4) and zero outside the image (the reference reads its zero-padded copies; a displacement
+// that leaves the image is skipped in gradSecond and multiplies a zero in gradFirst, exactly as there).
+// Reads are coalesced along x and served by L1 / L2 (every value is reused by the 81 displacements of its neighbours).
+__global__ void __launch_bounds__(256)
+correlation_bwd_kernel(const float *__restrict__ first, const float *__restrict__ second,
+                       const float *__restrict__ grad_out, int C, int H, int W, float *__restrict__ grad_first,
+                       float *__restrict__ grad_second) {
+    const int64_t plane = (int64_t)H * W;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (c, y, x) of sample b
+    if (e >= C * plane) return;
+    const int b = blockIdx.z;
+    const int c = (int)(e / plane);
+    const int r = (int)(e - c * plane);
+    const int y = r / W, x = r - y * W;
+    const float *f1 = first + ((int64_t)b * C + c) * plane, *f2 = second + ((int64_t)b * C + c) * plane;
+    const float *g = grad_out + (int64_t)b * kCorrD * kCorrD * plane;
+    float s1 = 0.f, s2 = 0.f;
+    for (int dy = -kCorrR; dy <= kCorrR; ++dy) {
+        for (int dx = -kCorrR; dx <= kCorrR; ++dx) {
+            const int op = (dy + kCorrR) * kCorrD + (dx + kCorrR);
+            const float *gp = g + (int64_t)op * plane;
+            if (grad_first) {
+                const int yy = y + dy, xx = x + dx;
+                const float bot1 = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(f2 + (int64_t)yy * W + xx) : 0.f;
+                s1 = fmaf(__ldg(gp + r), bot1, s1);
+            }
+            if (grad_second) {
+                const int yy = y - dy, xx = x - dx;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                    s2 = fmaf(__ldg(gp + (int64_t)yy * W + xx), __ldg(f1 + (int64_t)yy * W + xx), s2);
+            }
+        }
+    }
+    if (grad_first) grad_first[((int64_t)b * C + c) * plane + r] = s1 / (float)C;
+    if (grad_second) grad_second[((int64_t)b * C + c) * plane + r] = s2 / (float)C;
+}
+
 }  // namespace d4
 
 using namespace d4;
@@ -81,5 +126,16 @@ extern "C" int d4_correlation_fwd(const float *first, const float *second, int B
     dim3 grid(cdiv(W, kCorrTW), cdiv(H, kCorrTH), B);
     correlation_fwd_kernel<<<grid, kCorrTW * kCorrTH, 0, as_stream(stream)>>>(first, second, C, H, W, out);
     D4_CHECK_LAUNCH("d4_correlation_fwd");
+    return 0;
+}
+
+extern "C" int d4_correlation_bwd(const float *first, const float *second, const float *grad_out, int B, int C, int H,
+                                  int W, float *grad_first, float *grad_second, d4_stream_t stream) {
+    D4_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && B <= 65535, "d4_correlation_bwd: bad sizes");
+    if (B == 0 || (!grad_first && !grad_second)) return 0;
+    D4_CHECK_ARG(first && second && grad_out, "d4_correlation_bwd: null pointer");
+    dim3 grid(cdiv((int64_t)C * H * W, 256), 1, B);
+    correlation_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(first, second, grad_out, C, H, W, grad_first, grad_second);
+    D4_CHECK_LAUNCH("d4_correlation_bwd");
     return 0;
 }

@@ -360,9 +360,15 @@ int d4_densify_stats(const float *v_means2d, const int32_t *radii, int N, int G,
  * CuPy kernels kernel_Correlation_rearrange (:8-33, twice) + kernel_Correlation_updateOutput (:35-103), reached from
  * flow3d/models/pwcnet.py:179,187.  first / second [B,C,H,W] (NCHW, contiguous) -> out [B,81,H,W]:
  *   out[b, (dy+4)*9 + (dx+4), y, x] = (1/C) sum_c first[b,c,y,x] * second[b,c,y+dy,x+dx],  dx, dy in [-4,4],
- * zero outside the image.  Forward only: the reference evaluates PWC-Net under no_grad (loss_utils.py:171-172).   */
+ * zero outside the image.                                                                                          */
 int d4_correlation_fwd(const float *first, const float *second, int B, int C, int H, int W, float *out,
                        d4_stream_t stream);
+/* replaces _FunctionCorrelation.backward (correlation.py:336-385) and its kernels kernel_Correlation_updateGradFirst
+ * (:105-167) / kernel_Correlation_updateGradSecond (:169-233), one launch for the whole batch instead of two per
+ * sample.  grad_out [B,81,H,W] -> grad_first / grad_second [B,C,H,W] (either may be NULL); same summation order as the
+ * reference.  The reference's own caller never needs it (PWC-Net runs under no_grad, loss_utils.py:171-172).          */
+int d4_correlation_bwd(const float *first, const float *second, const float *grad_out, int B, int C, int H, int W,
+                       float *grad_first, float *grad_second, d4_stream_t stream);
 
 #ifdef __cplusplus
 }

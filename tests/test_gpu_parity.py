@@ -1068,7 +1068,7 @@ def test_correlation_f4_vs_oracle(B, C, H, W):
     """Row f4: the PWC-Net cost volume (flow3d/models/external/pwcnet/correlation/correlation.py:8-103) against the
     numpy restatement of the reference's CuPy kernels.  The kernel sums the C products per output in channel order,
     the reference in 32 interleaved lanes: agreement to fp32 round-off of a C-term dot product, held to 2e-6 of the
-    tensor scale (measured <= 4e-7)."""
+    tensor scale (measured <= 4e-7).  Then the backward against the restatement of the two gradient kernels."""
     from deblur4dgs_b200._cabi import D4Error
     from deblur4dgs_b200.correlation import FunctionCorrelation, ModuleCorrelation
     from oracle import correlation as ocorr
@@ -1082,7 +1082,18 @@ def test_correlation_f4_vs_oracle(B, C, H, W):
     e = scale_err(got.cpu().numpy(), ref)
     report(test=f"correlation_{B}x{C}x{H}x{W}", kind="correlation", scale_err=e)
     assert e <= 2e-6, e
-    with pytest.raises(D4Error):
-        FunctionCorrelation(a.to(DEV).requires_grad_(True), b.to(DEV))
+    # backward (kernel_Correlation_updateGradFirst / updateGradSecond, correlation.py:105-233): same summation order as
+    # the restatement, so the gradients agree to the last bits (held to 1e-6 of the tensor scale)
+    ga, gb = a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    go = torch.randn(B, 81, H, W, generator=g)
+    FunctionCorrelation(ga, gb).backward(go.to(DEV))
+    rf, rs = ocorr.correlation_backward(a.numpy(), b.numpy(), go.numpy())
+    e1, e2 = scale_err(ga.grad.cpu().numpy(), rf), scale_err(gb.grad.cpu().numpy(), rs)
+    report(test=f"correlation_{B}x{C}x{H}x{W}", kind="correlation_bwd", grad_first=e1, grad_second=e2,
+           bit_equal_first=bool(np.array_equal(ga.grad.cpu().numpy(), rf)), bit_equal_second=bool(np.array_equal(gb.grad.cpu().numpy(), rs)))
+    assert e1 <= 1e-6 and e2 <= 1e-6, (e1, e2)
+    only_first = a.to(DEV).requires_grad_(True)
+    FunctionCorrelation(only_first, b.to(DEV)).backward(go.to(DEV))
+    assert torch.equal(only_first.grad, ga.grad)
     with pytest.raises(D4Error):
         FunctionCorrelation(a, b)
