@@ -141,7 +141,7 @@ def algorithmic_bytes(G, Gf, K, D, P, I_per_frame, tiles):
 # ------------------------------------------------------------------------------------------ #
 # CPU arm: the oracle restatement on the host cores
 # ------------------------------------------------------------------------------------------ #
-def cpu_frame(sc, d0, sub_idx=0):
+def cpu_frame(sc, d0, sub_idx=0, keep=None):
     """One sub-exposure frame forward + backward on the CPU: reference-style deformation
     (oracle/deform.py, torch CPU) + oracle rasterizer (C/OpenMP).  Returns seconds."""
     import numpy as np
@@ -159,7 +159,10 @@ def cpu_frame(sc, d0, sub_idx=0):
     vM = torch.from_numpy(g["means"].astype("float32"))[None]
     vQ = torch.from_numpy(g["quats"].astype("float32"))[None]
     torch.autograd.backward([M, Q], [vM, vQ])
-    return time.perf_counter() - t0, int(meta["isect_ids"].shape[0])
+    dt = time.perf_counter() - t0
+    if keep is not None:  # the oracle's image of this sub-exposure, for the parity figure of the bench line
+        keep.update(img=rc[0], alpha=ra[0], edge=meta["edge"][0] != 0)
+    return dt, int(meta["isect_ids"].shape[0])
 
 
 def run_reference_arm(args):
@@ -420,6 +423,31 @@ def main():
         torch.cuda.synchronize()
         cap.check()
         graph_ms = g0.elapsed_time(g1) / args.steps
+    # ---- timed region 1c: forward only (SURVEY 8d asks for fwd-only and fwd+bwd separately) ----
+    fwd_ms = None
+    if world == 1:
+        def fwd_only():
+            with torch.no_grad():
+                p0 = {k: getattr(sc, k) for k in param_names}
+                sca, opa, col = assemble_gaussians(p0["fg_scales"], p0["bg_scales"], p0["fg_opacities"], p0["bg_opacities"],
+                                                   p0["fg_colors"], p0["bg_colors"],
+                                                   extra=sc.extra_channels if sc.extra_channels.shape[1] else None,
+                                                   with_mask=True)
+                render_subexposures(p0["fg_means"], p0["fg_quats"], p0["motion_coefs"], p0["bg_means"], p0["bg_quats"],
+                                    p0["rots"], p0["transls"], sc.times, sc.RTs, sca, opa, col, sc.w2c, sc.K, W, H,
+                                    backgrounds=bg, render_mode="RGB+ED", combine=True, ref_quirk=True, capacity=cap)
+        for _ in range(3):
+            fwd_only()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            fwd_only()
+        f1.record()
+        torch.cuda.synchronize()
+        fwd_ms = f0.elapsed_time(f1) / args.steps
+        if cap is not None:
+            cap.check()
     n_sort_passes = math.ceil((32 + _cabi.lib().d4_tile_n_bits(math.ceil(W / 16) * math.ceil(H / 16)) +
                                int(math.floor(math.log2(max(1, int(frames_per_step_local))))) + 1) / 8)
     if "d4_sort_pairs_u64" in prof:  # radix fallback only: 3 kernels per pass (the default bucketed binning has none)
@@ -632,6 +660,9 @@ def main():
                                                     "note": "the same step (fwd+bwd) replayed from one captured CUDA graph"},
             "clocks": clocks,
         }
+        if fwd_ms is not None:
+            line["fwd_only"] = {"ms_per_step": fwd_ms, "value": frames_per_step_global / (fwd_ms * 1e-3),
+                                "note": "forward only (no autograd graph, no hit words), same scene, inputs resident"}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import raster as orc
             cores = os.cpu_count() or 1
@@ -639,10 +670,45 @@ def main():
             orc.set_num_threads(cores)
             cpu_frame(sc_cpu, D0, 0)  # warm-up (page-in, OpenMP pool)
             n_cpu = 2
-            dts = [cpu_frame(sc_cpu, D0, i % sc_cpu.N)[0] for i in range(n_cpu)]
+            kept = {}
+            dts = [cpu_frame(sc_cpu, D0, i % sc_cpu.N, keep=kept if i == n_cpu - 1 else None)[0] for i in range(n_cpu)]
             line["cpu_baseline"] = {"value": n_cpu / sum(dts), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_cpu} sub-exposure frames fwd+bwd of {args.config} (1 warm-up), oracle port "
                                               "(torch-CPU deformation + C/OpenMP rasterizer), all host cores"}
+            # max image delta vs the oracle, on the benchmark scene itself (sub-exposure n_cpu - 1 at full
+            # size; pixels whose alpha / termination decision the oracle flags as knife-edge are excluded and counted)
+            import numpy as np
+            with torch.no_grad():
+                p0 = {k: getattr(sc, k) for k in param_names}
+                sca, opa, col = assemble_gaussians(p0["fg_scales"], p0["bg_scales"], p0["fg_opacities"], p0["bg_opacities"],
+                                                   p0["fg_colors"], p0["bg_colors"],
+                                                   extra=sc.extra_channels if sc.extra_channels.shape[1] else None,
+                                                   with_mask=True)
+                o = render_subexposures(p0["fg_means"], p0["fg_quats"], p0["motion_coefs"], p0["bg_means"], p0["bg_quats"],
+                                        p0["rots"], p0["transls"], sc.times, sc.RTs, sca, opa, col, sc.w2c, sc.K, W, H,
+                                        backgrounds=bg, render_mode="RGB+ED", combine=False)
+                i_sub = (n_cpu - 1) % sc_cpu.N
+                got = o["exposure_imgs"][i_sub, 0].cpu().numpy()
+                got_a = o["exposure_alphas"][i_sub, 0].cpu().numpy()
+            # the metrics of tests/test_gpu_parity.py::image_errors: pixels with alpha >= 0.05 ("solid") against the
+            # SURVEY 8(c) metric and per channel; fainter ones (alpha = 1 - T cancels, the expected depth divides by it)
+            # against 1e-3 of the tensor scale
+            ok = ~kept["edge"]
+            ref = kept["img"]
+            solid = ok & (kept["alpha"][..., 0] >= 0.05)
+            faint = ok & ~solid
+            d = np.abs(got - ref)
+            scale_ch = np.abs(ref).reshape(-1, ref.shape[-1]).max(axis=0)
+            scale_c = np.abs(ref).max()
+            line["parity"] = {
+                "sub_exposure": int(i_sub), "max_abs_image_delta": float(d[ok].max()),
+                "rel_err_per_channel": float((d[solid] / np.maximum(np.abs(ref[solid]), 1e-2 * scale_ch)).max()),
+                "rel_err_survey_8c": float((d[solid] / np.maximum(np.abs(ref[solid]), 1e-3 * scale_c)).max()),
+                "rel_err_faint_pixels": float((d[faint] / np.maximum(np.abs(ref[faint]), 1e-3 * scale_c)).max()) if faint.any() else 0.0,
+                "max_abs_alpha_delta": float(np.abs(got_a[ok] - kept["alpha"][ok]).max()),
+                "knife_edge_pixels_excluded": float(1.0 - ok.mean()),
+                "note": "GPU image of one full-size sub-exposure of the benchmark scene against the CPU oracle; same metrics as "
+                        "tests/test_gpu_parity.py::image_errors (bounds there: 1e-4 per channel, 3e-4 SURVEY 8c, 1e-4 faint)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
