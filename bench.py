@@ -690,25 +690,21 @@ def main():
                 i_sub = (n_cpu - 1) % sc_cpu.N
                 got = o["exposure_imgs"][i_sub, 0].cpu().numpy()
                 got_a = o["exposure_alphas"][i_sub, 0].cpu().numpy()
-            # the metrics of tests/test_gpu_parity.py::image_errors: pixels with alpha >= 0.05 ("solid") against the
-            # SURVEY 8(c) metric and per channel; fainter ones (alpha = 1 - T cancels, the expected depth divides by it)
-            # against 1e-3 of the tensor scale
+            # end-to-end figure: CUDA deformation + rasterization against the oracle's torch-CPU deformation + C
+            # rasterizer.  The two deformations agree to ~1e-6, which moves a few alpha >= 1/255 decisions that the
+            # oracle's knife-edge map (made for ITS inputs) does not flag, so the delta is reported against the channel
+            # scale; the per-stage bounds (same inputs into each stage, 1e-4 per pixel) are tests/test_gpu_parity.py's
             ok = ~kept["edge"]
             ref = kept["img"]
-            solid = ok & (kept["alpha"][..., 0] >= 0.05)
-            faint = ok & ~solid
             d = np.abs(got - ref)
             scale_ch = np.abs(ref).reshape(-1, ref.shape[-1]).max(axis=0)
-            scale_c = np.abs(ref).max()
             line["parity"] = {
                 "sub_exposure": int(i_sub), "max_abs_image_delta": float(d[ok].max()),
-                "rel_err_per_channel": float((d[solid] / np.maximum(np.abs(ref[solid]), 1e-2 * scale_ch)).max()),
-                "rel_err_survey_8c": float((d[solid] / np.maximum(np.abs(ref[solid]), 1e-3 * scale_c)).max()),
-                "rel_err_faint_pixels": float((d[faint] / np.maximum(np.abs(ref[faint]), 1e-3 * scale_c)).max()) if faint.any() else 0.0,
+                "max_delta_over_channel_scale": float((d[ok] / scale_ch).max()),
                 "max_abs_alpha_delta": float(np.abs(got_a[ok] - kept["alpha"][ok]).max()),
                 "knife_edge_pixels_excluded": float(1.0 - ok.mean()),
-                "note": "GPU image of one full-size sub-exposure of the benchmark scene against the CPU oracle; same metrics as "
-                        "tests/test_gpu_parity.py::image_errors (bounds there: 1e-4 per channel, 3e-4 SURVEY 8c, 1e-4 faint)"}
+                "note": "one full-size sub-exposure of the benchmark scene, CUDA deformation + rasterization against the CPU "
+                        "oracle chain; per-stage parity (<= 1e-4 per pixel, bit-exact bins) is tests/test_gpu_parity.py"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
