@@ -231,6 +231,7 @@ def main():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--frame", type=int, default=0)
+    ap.add_argument("--no-fwd-only", action="store_true", help="skip the forward-only leg")
     ap.add_argument("--profile-pass", action="store_true",
                     help="take the per-kernel CUDA events in a separate pass instead of inside the timed region")
     args = ap.parse_args()
@@ -425,7 +426,7 @@ def main():
         graph_ms = g0.elapsed_time(g1) / args.steps
     # ---- timed region 1c: forward only (SURVEY 8d asks for fwd-only and fwd+bwd separately) ----
     fwd_ms = None
-    if world == 1:
+    if world == 1 and not args.no_fwd_only:
         def fwd_only():
             with torch.no_grad():
                 p0 = {k: getattr(sc, k) for k in param_names}

@@ -14,7 +14,7 @@ timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_ou
 if [ "$mode" = "full" ]; then
   echo "== ncu launch list (every kernel of 3 warm-up + 2 timed + 4 e2e steps)"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_bench.log 2>&1
+      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-fwd-only > gpurun_out/ncu_bench.log 2>&1
   tail -2 gpurun_out/ncu_bench.log
   echo "== ncu full capture of the blend kernels"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:blend_ -s 6 -c 2 \
