@@ -396,6 +396,8 @@ def main():
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in prof.items()}
     # every kernel of a step: the library's own (per C-ABI call) + the zero-fills of the op code (torch kernels)
     own_launches_per_step = sum(len(v) * _cabi.LAUNCHES.get(k, 1) for k, v in prof.items()) / args.steps
+    if cap is not None and cap.sort_cap > 2048:  # long per-tile lists: the records are packed by a second kernel
+        own_launches_per_step += len(prof.get("d4_tile_sort_pack_cap", [])) / args.steps
     launches_per_step = own_launches_per_step + fills_per_step
     if cap is not None:
         cap.check()  # raises if any timed step overflowed the binning capacity

@@ -411,6 +411,18 @@ __device__ __forceinline__ void pack_segment(const PackArgs &p, IdAt id_at, int 
     if (tid == 0) p.rec_counts[seg] = run;
 }
 
+// The run of segment `seg` in the sorted lists and whether the tile sort could take it (capacity mode, see
+// tile_sort_kernel): shared by the sort and by the stand-alone packing pass that follows it for long lists.
+__device__ __forceinline__ bool segment_fits(const int32_t *__restrict__ tile_offsets, int64_t n_isects,
+                                             const int64_t *__restrict__ n_isects_dev, int64_t capacity, int sort_capacity,
+                                             int bucket_stride, int64_t n_segments, int64_t seg, int64_t &start64,
+                                             int64_t &end64) {
+    if (n_isects_dev) n_isects = *n_isects_dev;
+    start64 = tile_offsets[seg];
+    end64 = (seg == n_segments - 1) ? n_isects : (int64_t)tile_offsets[seg + 1];
+    return end64 <= capacity && end64 - start64 <= sort_capacity && (bucket_stride == 0 || end64 - start64 <= bucket_stride);
+}
+
 __global__ void __launch_bounds__(256)
 isect_pack_kernel(PackArgs p, const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
                   int64_t n_isects, int64_t n_segments, int n_tiles) {
@@ -419,6 +431,22 @@ isect_pack_kernel(PackArgs p, const int32_t *__restrict__ tile_offsets, const in
     const int32_t start = tile_offsets[seg];
     const int32_t end = (seg == n_segments - 1) ? (int32_t)n_isects : tile_offsets[seg + 1];
     pack_segment(p, [&](int i) { return __ldg(flatten_ids + start + i); }, end - start, start, seg, n_tiles, s_warp);
+}
+
+// packing pass after a tile sort that did not pack (long lists): same segment logic as tile_sort_kernel, but at eight
+// CTAs per SM -- the gathers of a batch are latency-bound and the sort's shared-memory footprint leaves 1-3 CTAs
+__global__ void __launch_bounds__(256)
+isect_pack_after_sort_kernel(PackArgs p, const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                             int64_t n_isects, const int64_t *__restrict__ n_isects_dev, int64_t capacity,
+                             int sort_capacity, int bucket_stride, int64_t n_segments, int n_tiles) {
+    __shared__ int32_t s_warp[8];
+    const int64_t seg = blockIdx.x;
+    int64_t start64, end64;
+    const bool fits = segment_fits(tile_offsets, n_isects, n_isects_dev, capacity, sort_capacity, bucket_stride, n_segments,
+                                   seg, start64, end64);
+    const int32_t start = (int32_t)start64;
+    const int n = fits ? (int)(end64 - start64) : 0;
+    pack_segment(p, [&](int i) { return __ldg(flatten_ids + start + i); }, n, start, seg, n_tiles, s_warp);
 }
 
 __global__ void __launch_bounds__(256, 8)  // 32 registers: eight CTAs per SM for the short lists of the benchmark scene
@@ -433,12 +461,10 @@ tile_sort_kernel(const uint64_t *__restrict__ bucket_keys, const int32_t *__rest
     // capacity mode (n_isects_dev != null): the intersection count lives on the device, the buffers hold `capacity`
     // entries and the shared-memory sort `sort_capacity` keys; a tile that does not fit is dropped (no records) and
     // *overflow is raised for the host to see later -- no device -> host sync inside the step
-    if (n_isects_dev) n_isects = *n_isects_dev;
-    const int64_t start64 = tile_offsets[seg];
-    const int64_t end64 = (seg == n_segments - 1) ? n_isects : (int64_t)tile_offsets[seg + 1];
+    int64_t start64, end64;
+    const bool fits = segment_fits(tile_offsets, n_isects, n_isects_dev, capacity, sort_capacity, bucket_stride, n_segments,
+                                   seg, start64, end64);
     // fixed-stride buckets: the unsorted keys of the segment sit at bucket_keys[seg * bucket_stride ...]
-    const bool fits = end64 <= capacity && end64 - start64 <= sort_capacity &&
-                      (bucket_stride == 0 || end64 - start64 <= bucket_stride);
     const uint64_t *src_keys = bucket_stride > 0 ? bucket_keys + seg * (int64_t)bucket_stride : bucket_keys + start64;
     (void)bucket_counts;
     if (!fits && overflow && threadIdx.x == 0) *overflow = 1;
@@ -660,10 +686,19 @@ static int launch_tile_sort(const char *name, const uint64_t *bucket_keys, const
         return 1;
     }
     const int64_t n_seg = (int64_t)C * tile_w * tile_h;
+    // long lists: the records are packed by a second kernel at full occupancy (c5 x2: 9.3 ms fused)
+    const bool split_pack = p.recs != nullptr && n_pad > 2048;
+    PackArgs p_sort = p;
+    if (split_pack) p_sort.recs = nullptr;
     tile_sort_kernel<<<(unsigned)n_seg, 256, smem, st>>>(bucket_keys, tile_offsets, n_isects, n_isects_dev, capacity, n_pad,
                                                         overflow, n_seg, tile_w * tile_h, d4_tile_n_bits(tile_w * tile_h),
-                                                        isect_ids, flatten_ids, p, nullptr, bucket_stride);
+                                                        isect_ids, flatten_ids, p_sort, nullptr, bucket_stride);
     D4_CHECK_LAUNCH(name);
+    if (split_pack) {
+        isect_pack_after_sort_kernel<<<(unsigned)n_seg, 256, 0, st>>>(p, tile_offsets, flatten_ids, n_isects, n_isects_dev,
+                                                                     capacity, n_pad, bucket_stride, n_seg, tile_w * tile_h);
+        D4_CHECK_LAUNCH(name);
+    }
     return 0;
 }
 
