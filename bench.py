@@ -33,6 +33,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The step allocates a few very large tensors (the N-image stack is 564 MB at c3) next to many small ones.  Without a
+# split limit the caching allocator carves small requests out of a free 564 MB block, so that a later stack request
+# finds no whole block and falls back to cudaMalloc -- an implicit device sync in the middle of the end-to-end loop
+# (seen once per ~15 steps).  Blocks above 128 MB are therefore never split.
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "max_split_size_mb:128")
+
 import torch  # noqa: E402
 
 METRIC = "rendered sub-exposure frames/sec at 720x1280, 300k Gaussians (fwd+bwd)"
@@ -510,7 +516,10 @@ def main():
             pending[buf][0].synchronize()  # the pinned buffer of step k-2 is free again
         t.append(time.perf_counter())
         if trace is not None:
-            t.append(torch.cuda.memory_stats().get("num_device_alloc", 0))
+            st_ = torch.cuda.memory_stats()
+            t.append(f"{st_.get('num_device_alloc', 0)} (reserved small {st_.get('reserved_bytes.small_pool.current', 0) >> 20} MiB, "
+                     f"large {st_.get('reserved_bytes.large_pool.current', 0) >> 20} MiB, allocated small "
+                     f"{st_.get('allocated_bytes.small_pool.current', 0) >> 10} KiB)")
             trace.append(t)
         ready = torch.cuda.Event()
         ready.record()
@@ -526,7 +535,7 @@ def main():
 
     # warm-up of THIS loop (two live output sets change the caching allocator's steady state); the JSON line reports the
     # cudaMalloc calls inside the timed region -- each is an implicit device sync -- and it must be 0
-    for k in range(max(4, args.warmup)):
+    for k in range(max(8, args.warmup)):
         e2e_step(k)
     torch.cuda.synchronize()
     uploaded.clear()  # the timed region uploads every one of its steps itself
