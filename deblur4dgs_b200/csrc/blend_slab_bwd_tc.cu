@@ -122,51 +122,10 @@ blend_bwd_slab_tc_kernel(SlabArgs a, const float *__restrict__ render_alphas, co
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const int64_t pid = ((int64_t)c * a.height + i) * a.width + j;
 
-    // ---- per-pixel state
-    constexpr int D2 = D0 / 2;
-    [[maybe_unused]] float2 v2[TC1 ? 1 : D2];  // colour cotangent as fp32x2 pairs (SIMT phase 1 only)
-    float vd = 0.f;                            // depth cotangent (after the ED normalisation backward)
-    float T_final = 1.f, v_ra = 0.f, bgdot = 0.f;
+    // ---- step 1 of the prologue: where the stream starts.  Only last_ids is needed for that, so it is fetched alone
+    // and the CTA meets once; the producer then streams the first stages WHILE the pixels fetch their cotangents
     int32_t bin_final = -1;
-    if (!producer) {
-        float v_out[D];
-        if (inside) {
-            const float alpha_px = render_alphas[pid];
-            T_final = 1.0f - alpha_px;
-            bin_final = last_ids[pid];
-            v_ra = v_render_alphas[pid];
-#pragma unroll
-            for (int k = 0; k < D; ++k) v_out[k] = __ldg(v_render_colors + pid * D + k);
-            if constexpr (DEPTH) {
-                if (a.normalize_depth) {
-                    const float ac = fmaxf(alpha_px, 1e-10f);
-                    const float vdd = v_out[D - 1];
-                    v_out[D - 1] = vdd / ac;
-                    if (alpha_px > 1e-10f) v_ra += -vdd * acc_depth[pid] / (ac * ac);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) v_out[k] = 0.f;
-        }
-        if (a.backgrounds) {
-#pragma unroll
-            for (int k = 0; k < D0; ++k) bgdot = fmaf(__ldg(a.backgrounds + (int64_t)c * D0 + k), v_out[k], bgdot);
-        }
-        if constexpr (!TC1) {
-#pragma unroll
-            for (int k2 = 0; k2 < D2; ++k2) v2[k2] = make_float2(v_out[2 * k2], v_out[2 * k2 + 1]);
-        }
-        if constexpr (DEPTH) vd = v_out[D - 1];
-        // the B operand of both contractions: 16-byte piece q of this pixel's row at piece position q ^ (vsw >> 2)
-        float *vo = s_vout + tid * D0;
-        const int pk = vsw(lane) >> 2;
-#pragma unroll
-        for (int k4 = 0; k4 < D0 / 4; ++k4)
-            *reinterpret_cast<float4 *>(vo + 4 * (k4 ^ pk)) =
-                make_float4(v_out[4 * k4], v_out[4 * k4 + 1], v_out[4 * k4 + 2], v_out[4 * k4 + 3]);
-        if constexpr (DEPTH) s_vd[tid] = vd;
-    }
+    if (inside) bin_final = last_ids[pid];
     const int32_t warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
     if (!producer && lane == 0) s_max[w] = warp_bin_final;
     if (tid == 0) {
@@ -206,6 +165,52 @@ blend_bwd_slab_tc_kernel(SlabArgs a, const float *__restrict__ render_alphas, co
         }
         return;  // every consumer waits for every stage: no copy is in flight when the CTA retires
     }
+
+    // ---- step 2 (consumer warps): per-pixel state.  A warp only ever reads the cotangent rows of its OWN 32 pixels
+    // (s_vw, s_vd + w * 32), so a warp barrier orders these stores -- no second CTA barrier
+    constexpr int D2 = D0 / 2;
+    [[maybe_unused]] float2 v2[TC1 ? 1 : D2];  // colour cotangent as fp32x2 pairs (SIMT phase 1 only)
+    float vd = 0.f;                            // depth cotangent (after the ED normalisation backward)
+    float T_final = 1.f, v_ra = 0.f, bgdot = 0.f;
+    {
+        float v_out[D];
+        if (inside) {
+            const float alpha_px = render_alphas[pid];
+            T_final = 1.0f - alpha_px;
+            v_ra = v_render_alphas[pid];
+#pragma unroll
+            for (int k = 0; k < D; ++k) v_out[k] = __ldg(v_render_colors + pid * D + k);
+            if constexpr (DEPTH) {
+                if (a.normalize_depth) {
+                    const float ac = fmaxf(alpha_px, 1e-10f);
+                    const float vdd = v_out[D - 1];
+                    v_out[D - 1] = vdd / ac;
+                    if (alpha_px > 1e-10f) v_ra += -vdd * acc_depth[pid] / (ac * ac);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) v_out[k] = 0.f;
+        }
+        if (a.backgrounds) {
+#pragma unroll
+            for (int k = 0; k < D0; ++k) bgdot = fmaf(__ldg(a.backgrounds + (int64_t)c * D0 + k), v_out[k], bgdot);
+        }
+        if constexpr (!TC1) {
+#pragma unroll
+            for (int k2 = 0; k2 < D2; ++k2) v2[k2] = make_float2(v_out[2 * k2], v_out[2 * k2 + 1]);
+        }
+        if constexpr (DEPTH) vd = v_out[D - 1];
+        // the B operand of both contractions: 16-byte piece q of this pixel's row at piece position q ^ (vsw >> 2)
+        float *vo = s_vout + tid * D0;
+        const int pk = vsw(lane) >> 2;
+#pragma unroll
+        for (int k4 = 0; k4 < D0 / 4; ++k4)
+            *reinterpret_cast<float4 *>(vo + 4 * (k4 ^ pk)) =
+                make_float4(v_out[4 * k4], v_out[4 * k4 + 1], v_out[4 * k4 + 2], v_out[4 * k4 + 3]);
+        if constexpr (DEPTH) s_vd[tid] = vd;
+    }
+    __syncwarp();
 
     // ---------------------------------------------------------------------------------------- consumer warps
     // constant part of dL/dalpha_i * (1 - alpha_i):  T_final * (v_alpha_out - bg.v_out)
