@@ -214,11 +214,12 @@ def test_rasterization_c1_config():
     check_raster_against("c1", inp, sc.width, sc.height, "RGB+ED", oracle_ref(inp, sc.width, sc.height, "RGB+ED"))
 
 
-@pytest.mark.parametrize("cfg", ["c2", "c3"])
+@pytest.mark.parametrize("cfg", ["c2", "c3", "c5"])
 def test_rasterization_baseline_configs_vs_oracle(cfg):
-    """BASELINE.json configs[1] / configs[2] at FULL size: the middle sub-exposure of the deformed scene (100 k
-    Gaussians at 288x512 / 300 k at 720x1280, D = 17, 'RGB+ED'), forward and backward against the C oracle --
-    bins bit-exact, images <= 1e-4, every leaf gradient.  The oracle needs ~1 s for this on the box's host cores."""
+    """BASELINE.json configs[1] / configs[2] / configs[4] at FULL size: the middle sub-exposure of the deformed scene
+    (100 k Gaussians at 288x512 / 300 k at 720x1280 / 1 M at 720x1280 -- 5 M intersections, per-tile lists beyond 1024
+    entries, i.e. the merge path of the tile sort --, D = 17, 'RGB+ED'), forward and backward against the C oracle --
+    bins bit-exact, images <= 1e-4, every leaf gradient.  The oracle needs 1-4 s for this on the box's host cores."""
     sc = make_config(cfg)
     i = sc.N // 2
     M, Q = odef.deform_subexposures(sc.fg_means, sc.fg_quats, sc.motion_coefs, sc.bg_means, sc.bg_quats, sc.rots,
