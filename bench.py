@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--frame", type=int, default=0)
     ap.add_argument("--no-fwd-only", action="store_true", help="skip the forward-only leg")
+    ap.add_argument("--no-strong", action="store_true", help="multi-GPU: skip the strong-scaling leg")
     ap.add_argument("--profile-pass", action="store_true",
                     help="take the per-kernel CUDA events in a separate pass instead of inside the timed region")
     args = ap.parse_args()
@@ -535,7 +536,7 @@ def main():
 
     # warm-up of THIS loop (two live output sets change the caching allocator's steady state); the JSON line reports the
     # cudaMalloc calls inside the timed region -- each is an implicit device sync -- and it must be 0
-    for k in range(max(8, args.warmup)):
+    for k in range(max(16, args.warmup)):
         e2e_step(k)
     torch.cuda.synchronize()
     uploaded.clear()  # the timed region uploads every one of its steps itself
@@ -550,25 +551,29 @@ def main():
         e2e_step(k)
     torch.cuda.current_stream().wait_stream(copy_stream)  # the last downloads are part of the timed region
     e1.record()
+    # cudaMalloc calls inside the region (allocation is host-synchronous: every one of the loop has happened by now;
+    # read before the closing barrier, whose own first-use allocation is not part of the timed steps)
+    e2e_mallocs = torch.cuda.memory_stats().get("num_device_alloc", 0) - allocs0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e2e_mallocs = torch.cuda.memory_stats().get("num_device_alloc", 0) - allocs0  # cudaMalloc calls inside the region
     if trace:
         for k, t in enumerate(trace[-args.steps:]):
             d = [1e3 * (b - a) for a, b in zip(t[:4], t[1:4])]
             print(f"e2e step {k}: upload {d[0]:.2f} enqueue {d[1]:.2f} wait(k-2 download) {d[2]:.2f} ms; "
                   f"cudaMallocs so far {t[4]}", file=sys.stderr)
     uploaded.clear()  # (the look-ahead upload of the step after the last one is not counted in h2d_bytes_per_step)
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ms2 = torch.tensor([e0.elapsed_time(e1), float(e2e_mallocs)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_mallocs = int(ms2[1].item())  # max over ranks
+    ms2 = ms2[:1]
     e2e_value = frames_per_step_global * args.steps / (float(ms2.item()) * 1e-3)
 
     # ---- timed region 3 (multi-GPU frames runs): STRONG scaling of ONE blurry frame -- BASELINE configs[3] --------
     # the frame's N x world (sub-exposure, tile-row band) units over the ranks, image / extrema / gradient all-reduce
     strong = None
-    if world > 1 and args.shard == "frames":
+    if world > 1 and args.shard == "frames" and not args.no_strong:
         # the SAME frame on every rank
         sc_frame = make_config(args.config, seed=seed, scale_mult=args.scale_mult).to(dev) if not args.checkpoint else sc
 
