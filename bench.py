@@ -446,16 +446,18 @@ def main():
                 render_subexposures(p0["fg_means"], p0["fg_quats"], p0["motion_coefs"], p0["bg_means"], p0["bg_quats"],
                                     p0["rots"], p0["transls"], sc.times, sc.RTs, sca, opa, col, sc.w2c, sc.K, W, H,
                                     backgrounds=bg, render_mode="RGB+ED", combine=True, ref_quirk=True, capacity=cap)
-        for _ in range(3):
+        for _ in range(8):  # the allocator settles on the forward-only pattern (no saved tensors) within a few steps
             fwd_only()
         torch.cuda.synchronize()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fwd_allocs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
         f0.record()
         for _ in range(args.steps):
             fwd_only()
         f1.record()
         torch.cuda.synchronize()
         fwd_ms = f0.elapsed_time(f1) / args.steps
+        fwd_mallocs = torch.cuda.memory_stats().get("num_device_alloc", 0) - fwd_allocs0
         if cap is not None:
             cap.check()
     n_sort_passes = math.ceil((32 + _cabi.lib().d4_tile_n_bits(math.ceil(W / 16) * math.ceil(H / 16)) +
@@ -679,6 +681,7 @@ def main():
         }
         if fwd_ms is not None:
             line["fwd_only"] = {"ms_per_step": fwd_ms, "value": frames_per_step_global / (fwd_ms * 1e-3),
+                                "cuda_mallocs_in_timed_region": int(fwd_mallocs),
                                 "note": "forward only (no autograd graph, no hit words), same scene, inputs resident"}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import raster as orc
