@@ -153,3 +153,37 @@ def test_camera_se3_pinned_to_reference_and_interp(hh):
         hh.hh_camera_interp_vjp(_p(sn), _p(en), _p(us), N, _p(vn), _p(g12))
         refg = np.concatenate([gs.numpy(), ge.numpy()])
         assert scale_err(g12, refg) < 2e-3, (scale, g12, refg)
+
+
+def test_3xtf32_split_is_fp32_grade():
+    """The tensor-core backward (csrc/blend_slab_bwd_tc.cu) feeds mma.sync.m16n8k8 TF32 with a = a_hi + a_lo,
+    b = b_hi + b_lo (hi = the value truncated to TF32's 10 mantissa bits, lo = the exact fp32 remainder, itself
+    truncated by the MMA) and accumulates a_lo b_hi + a_hi b_lo + a_hi b_hi in fp32.  Emulated here in numpy: the
+    dropped terms are bounded by 2^-21 |a||b| per product, i.e. the contraction over 32 pixels stays within ~1e-6 of the
+    exact sum relative to sum |a||b| -- the same order as a plain fp32 FMA chain, which is why the parity tolerances did
+    not move when the contractions went to the tensor cores."""
+    rng = np.random.default_rng(0)
+
+    def tf32(x):
+        return (x.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    worst = 0.0
+    for scale in (1.0, 1e-3, 37.0):
+        a = (rng.standard_normal((4096, 32)) * scale).astype(np.float32)
+        b = rng.standard_normal((4096, 32)).astype(np.float32)
+        a_hi, b_hi = tf32(a), tf32(b)
+        a_lo, b_lo = tf32(a - a_hi), tf32(b - b_hi)  # a - a_hi is exact in fp32; the MMA truncates the operand again
+        assert np.array_equal(a_hi + (a - a_hi), a)
+        acc = np.zeros(4096, np.float32)
+        for k in range(32):  # fp32 accumulation, products of TF32 operands are exact in fp32
+            for x, y in ((a_lo, b_hi), (a_hi, b_lo), (a_hi, b_hi)):
+                acc = (acc + x[:, k] * y[:, k]).astype(np.float32)
+        exact = (a.astype(np.float64) * b.astype(np.float64)).sum(1)
+        mass = (np.abs(a).astype(np.float64) * np.abs(b)).sum(1)
+        worst = max(worst, float((np.abs(acc - exact) / mass).max()))
+        plain = np.zeros(4096, np.float32)
+        for k in range(32):
+            plain = (plain + a[:, k] * b[:, k]).astype(np.float32)
+        plain_err = float((np.abs(plain - exact) / mass).max())
+        assert worst <= 4 * max(plain_err, 2.0 ** -22), (scale, worst, plain_err)
+    assert worst <= 1.5e-6, worst
